@@ -1,0 +1,228 @@
+/*
+ * b2s.h -- C ABI of libb2s.so, the B200-native (sm_100a) sparse-voxel hot path.
+ *
+ * This is the drop-in boundary for the two reference interfaces of the path
+ * (SURVEY.md section 8(b)):
+ *   #1  the MinkowskiEngine Python surface used by minsu3d
+ *       (minsu3d/model/module/common.py:12-93, backbone.py:14-38,
+ *        general_model.py:187-191, data/dataset/general_dataset.py:159-163)
+ *   #2  the COMMON_OPS pybind module
+ *       (minsu3d/common_ops/src/common_ops_api.cpp:6-29)
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types.  Every pointer is a DEVICE pointer
+ *     unless its name starts with h_.
+ *   - every entry point takes the caller's stream and never synchronises it;
+ *     sizes that are only known on the device are written to a device int32
+ *     (d_count ...) which the host reads back when it needs a shape.
+ *   - the library never allocates: scratch comes from the caller (ws, ws_bytes);
+ *     each op with scratch has a *_ws_bytes() query.
+ *   - return value: 0 = ok, <0 = B2S_E_* (no exit(), cf. the reference's
+ *     exit(-1) in bfs_cluster.cu:82-86 / hierarchical_aggregation.cu:198-203).
+ *   - re-entrant, no global state: one process per GPU works unchanged.
+ */
+#ifndef B2S_H
+#define B2S_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* b2s_stream_t;
+
+#define B2S_OK 0
+#define B2S_E_INVALID (-1)   /* bad argument (shape, null pointer, unsupported size) */
+#define B2S_E_WORKSPACE (-2) /* workspace too small */
+#define B2S_E_LAUNCH (-3)    /* cudaGetLastError() != cudaSuccess after a launch */
+#define B2S_E_RANGE (-4)     /* coordinate outside the packable range */
+
+/* library / build info: returns the compiled SM arch (100) */
+int b2s_version(void);
+const char* b2s_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * T1 / V1 -- coordinate hash: insert + first-occurrence unique + inverse map.
+ * Replaces ME.SparseTensor's coordinate-manager insert and ME.utils.sparse_quantize's
+ * unique/inverse (general_dataset.py:159-163, general_model.py:187-189), and -- with
+ * quant > 1 -- the strided coordinate map of MinkowskiConvolution(k=2,s=2) (common.py:69).
+ *
+ *   coords      [n,4] int32 (b,x,y,z)
+ *   quant       spatial quantisation: key coords are floor(c/quant)*quant (1 = identity)
+ *   table_keys  [cap] uint64, table_vals [cap] int32, cap = b2s_hash_capacity(n) (power of two)
+ *   unique_idx  [n] int32 (first m valid): input row of each unique coordinate, ascending
+ *   inverse     [n] int32: unique row of every input row
+ *   out_coords  [n,4] int32 (first m valid): quantised coordinates of the unique rows
+ *   d_count     int32[2] on device: {m, range_error_flag}
+ * After the call the table maps packed coordinate -> unique row.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t b2s_hash_capacity(int64_t n);
+size_t b2s_coord_unique_ws_bytes(int64_t n);
+int b2s_coord_unique(const int32_t* coords, int64_t n, int32_t quant,
+                     uint64_t* table_keys, int32_t* table_vals, int64_t cap,
+                     int32_t* unique_idx, int32_t* inverse, int32_t* out_coords,
+                     int32_t* d_count, void* ws, size_t ws_bytes, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * T2 -- kernel map (output-stationary neighbour table).
+ * nbr[o*K + kidx] = input row whose coordinate equals out_coords[o] + offset(kidx), or -1.
+ * Offsets enumerate x fastest: odd ksize: (i-(ksize-1)/2)*dil, even ksize: i*dil
+ * (SURVEY.md appendix A.4).  K = ksize^3.  The table is the input map's hash table.
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_kernel_map(const int32_t* out_coords, int64_t n_out, int32_t ksize, int32_t dil,
+                   const uint64_t* table_keys, const int32_t* table_vals, int64_t cap,
+                   int32_t* nbr, b2s_stream_t stream);
+
+/* Canonical per-offset pair lists (sorted by kidx, then by output row) from a neighbour table.
+ *   pair_in/pair_out [>= number of pairs] int32, k_offsets [K+1] int32 (CSR over kidx),
+ *   d_count int32[1] = total pairs.  Upper bound on pairs: n_out*K.                              */
+size_t b2s_pairs_ws_bytes(int64_t n_out, int32_t K);
+int b2s_pairs_from_nbr(const int32_t* nbr, int64_t n_out, int32_t K, int64_t pair_capacity,
+                       int32_t* pair_in, int32_t* pair_out, int32_t* k_offsets, int32_t* d_count,
+                       void* ws, size_t ws_bytes, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * T3 / T4 -- sparse convolution (MinkowskiConvolution / MinkowskiConvolutionTranspose,
+ * common.py:12,31,37,40,69,77; backbone.py:14).  fp32 in / fp32 out.
+ *
+ * b2s_conv_table: out[o,:] = sum_k  A[nbr[o*K+k], :] @ Wk      (k ascending, -1 rows skipped)
+ *     Wk = W[kk] (c_in x c_out, row-major) or its transpose when w_transposed (then W is
+ *     [K, c_out, c_in] and the contraction runs over W's last axis), kk = k or K-1-k (k_reversed).
+ *     nbr == NULL means K == 1 and the identity map (1x1 convolution = dense matmul).
+ *     forward: (A=in, W) ; data gradient of a stride-1 conv: (A=grad_out, w_transposed, k_reversed).
+ * b2s_conv_pairs: for every pair p in [k_offsets[k], k_offsets[k+1]):
+ *     out[dst[p], :] = A[src[p], :] @ Wk   (each dst row appears once; plain store)
+ *     transposed-conv forward and strided-conv data gradient.
+ * b2s_conv_wgrad: gW[k] (+)= sum_p A[src[p], :]^T @ G[dst[p], :]   (gW zeroed by the callee)
+ * algo: 0 = auto, 1 = fp32 FMA (SIMT), 2 = tcgen05 TF32x3 (fp32-class accuracy), 3 = tcgen05 TF32.
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, float* out,
+                   int64_t n_out, int32_t K, int32_t c_in, int32_t c_out,
+                   int32_t w_transposed, int32_t k_reversed, int32_t algo, b2s_stream_t stream);
+int b2s_conv_pairs(const float* A, const float* W, const int32_t* src, const int32_t* dst,
+                   const int32_t* k_offsets, float* out, int32_t K, int32_t c_in, int32_t c_out,
+                   int32_t w_transposed, int64_t max_pairs, int32_t algo, b2s_stream_t stream);
+int b2s_conv_wgrad(const float* A, const float* G, const int32_t* src, const int32_t* dst,
+                   const int32_t* k_offsets, float* gW, int32_t K, int32_t c_a, int32_t c_g,
+                   int64_t max_pairs, int32_t algo, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * T5 -- fused BatchNorm(+ReLU) on sparse-tensor features (MinkowskiBatchNorm + MinkowskiReLU,
+ * common.py:13-14,35-39).  Training statistics are biased batch statistics like
+ * torch.nn.BatchNorm1d.  stats = [2,C] float (mean, rstd) output of bn_stats.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b2s_bn_ws_bytes(int64_t n, int32_t c);
+int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float* mean, float* var_biased,
+                 void* ws, size_t ws_bytes, b2s_stream_t stream);
+int b2s_bn_apply(const float* x, int64_t n, int32_t c, const float* mean, const float* rstd,
+                 const float* gamma, const float* beta, int32_t relu, float* y, b2s_stream_t stream);
+/* backward of y = relu?(gamma*(x-mean)*rstd + beta) in training mode:
+ * dgamma, dbeta [C]; dx [n,C].  y is the forward output (for the ReLU mask).                     */
+int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, int32_t c,
+                    const float* mean, const float* rstd, const float* gamma, int32_t relu,
+                    int32_t training, float* dx, float* dgamma, float* dbeta,
+                    void* ws, size_t ws_bytes, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * V2 -- devoxelise gather and its scatter-add gradient (backbone.py:40, pointgroup.py:88).
+ * idx is int64 (voxel_point_map dtype, data_module.py:65).
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_gather_rows(const float* feat, const int64_t* idx, int64_t n, int32_t c, float* out,
+                    b2s_stream_t stream);
+int b2s_scatter_add_rows(const float* grad, const int64_t* idx, int64_t n, int32_t c,
+                         float* gfeat /* pre-zeroed [m,c] */, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * C1 -- ballquery_batch_p (bfs_cluster.cu:15-91, functions/common_ops.py:11-47).
+ * Neighbours k of p: same scene, fma(dz,dz,fma(dx,dx,dy*dy)) < r*r in fp32, ascending k,
+ * at most 1000 (the lowest 1000).  Canonical CSR: start = exclusive scan of len.
+ *   count: fills start_len [n,2] int32 and d_count[0] = nActive; keeps a cell grid in ws.
+ *   fill : writes idx [nActive] int32 using the same ws.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b2s_ballquery_ws_bytes(int64_t n);
+int b2s_ballquery_count(const float* xyz, const uint8_t* batch_idxs, const int32_t* batch_offsets,
+                        int64_t n, int32_t n_batch, float radius, int32_t* start_len,
+                        int32_t* d_count, void* ws, size_t ws_bytes, b2s_stream_t stream);
+int b2s_ballquery_fill(const float* xyz, const uint8_t* batch_idxs, const int32_t* batch_offsets,
+                       int64_t n, int32_t n_batch, float radius, const int32_t* start_len,
+                       int32_t* idx, void* ws, size_t ws_bytes, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * C2 / C3 / C4 -- BFS clustering on the GPU (bfs_cluster.cpp:28-187,
+ * hierarchical_aggregation.cpp:8-97).  Bit-exact with the reference's sequential BFS:
+ * cluster = set reachable from the lowest unvisited seed, clusters in seed order,
+ * points inside a cluster in BFS visit order.
+ *
+ * b2s_cluster_label : comp[v] = lowest index that reaches v (labels == NULL: no label test).
+ * b2s_cluster_select: sizes, keep mask, compaction.  mode 0: keep size >= thr_i (pg);
+ *     mode 1: keep (float)size >= thr_f (sg).  mode 2 (HAIS): class thresholds from
+ *     point_num_avg; cls: 0 = dropped, 1 = kept fragment, 2 = primary; fragments (size < high)
+ *     are also listed when want_fragments.
+ *     Outputs: d_count = {nCluster, sumNPoint}, cluster_offsets [nCluster+1], seeds [nCluster].
+ * b2s_cluster_order : cluster_idxs [sumNPoint,2] (cluster id, point) in BFS visit order.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b2s_cluster_ws_bytes(int64_t n);
+int b2s_cluster_label(const int32_t* nbr_idx, const int32_t* start_len, const int16_t* labels,
+                      int64_t n, int32_t* comp, void* ws, size_t ws_bytes, b2s_stream_t stream);
+int b2s_cluster_select(const int32_t* comp, const int16_t* labels, int64_t n, int32_t mode,
+                       int32_t thr_i, float thr_f, const float* point_num_avg, int32_t group,
+                       int32_t* cluster_offsets, int32_t* seeds, int32_t* d_count,
+                       void* ws, size_t ws_bytes, b2s_stream_t stream);
+int b2s_cluster_order(const int32_t* nbr_idx, const int32_t* start_len, const int16_t* labels,
+                      const int32_t* comp, int64_t n, const int32_t* cluster_offsets,
+                      const int32_t* seeds, int32_t n_cluster, int32_t* cluster_idxs,
+                      void* ws, size_t ws_bytes, b2s_stream_t stream);
+/* HAIS: centres [nCluster,5] = (sum_x/size, sum_y/size, sum_z/size, cls, batch), sums taken
+ * sequentially in BFS order in fp32 (hierarchical_aggregation.cpp:13-37,85-89).                  */
+int b2s_cluster_centers(const int32_t* cluster_idxs, const int32_t* cluster_offsets,
+                        int32_t n_cluster, const float* coords, const int16_t* labels,
+                        const uint8_t* batch_idxs, float* centers, b2s_stream_t stream);
+/* HAIS set aggregation (hierarchical_aggregation.cu:20-91): assign[f] = primary absorbing
+ * fragment f or -1; then concatenation primary points + absorbed fragments (ascending f).        */
+int b2s_ha_assign(const float* frag_centers, int32_t n_frag, const float* prim_centers,
+                  const int32_t* prim_offsets, int32_t n_prim, const float* radius_avg,
+                  int32_t* assign, b2s_stream_t stream);
+size_t b2s_ha_concat_ws_bytes(int32_t n_frag, int32_t n_prim);
+int b2s_ha_concat(const int32_t* frag_idxs, const int32_t* frag_offsets, int32_t n_frag,
+                  const int32_t* prim_idxs, const int32_t* prim_offsets, int32_t n_prim,
+                  const int32_t* assign, int32_t* out_idxs, int32_t* out_offsets,
+                  void* ws, size_t ws_bytes, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * S1 / S2 / S3 -- segmented reductions (sec_mean.cu:12-85, roipool.cu:12-120).
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_sec_mean(const float* inp, const int32_t* offsets, float* out, int32_t n_seg, int32_t c,
+                 b2s_stream_t stream);
+int b2s_sec_min(const float* inp, const int32_t* offsets, float* out, int32_t n_seg, int32_t c,
+                b2s_stream_t stream);
+int b2s_sec_max(const float* inp, const int32_t* offsets, float* out, int32_t n_seg, int32_t c,
+                b2s_stream_t stream);
+int b2s_roipool_fp(const float* feats, const int32_t* offsets, float* out, int32_t* maxidx,
+                   int32_t n_seg, int32_t c, b2s_stream_t stream);
+int b2s_roipool_bp(float* d_feats, const int32_t* offsets, const int32_t* maxidx,
+                   const float* d_out, int32_t n_seg, int32_t c, b2s_stream_t stream);
+int b2s_global_avg_pool_fp(const float* feats, const int32_t* offsets, float* out, int32_t n_seg,
+                           int32_t c, b2s_stream_t stream);
+int b2s_global_avg_pool_bp(float* d_feats, const int32_t* offsets, const float* d_out,
+                           int32_t n_seg, int32_t c, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * I1 / I2 -- proposal x instance IoU and mask labels (get_iou.cu:12-37,
+ * cal_iou_and_masklabel.cu:14-140).  mask_scores == NULL: all proposal points count.
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_get_iou(const int32_t* proposals_idx, const int32_t* proposals_offset,
+                const int16_t* instance_labels, const int32_t* instance_pointnum,
+                const float* mask_scores, float* proposals_iou, int32_t n_instance,
+                int32_t n_proposal, b2s_stream_t stream);
+int b2s_get_mask_label(const int32_t* proposals_idx, const int32_t* proposals_offset,
+                       const int16_t* instance_labels, const int16_t* instance_cls,
+                       const float* proposals_iou, int32_t n_instance, int32_t n_proposal,
+                       int32_t ignored_label, float iou_thr, uint8_t* mask_label,
+                       uint8_t* mask_label_mask, b2s_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H */

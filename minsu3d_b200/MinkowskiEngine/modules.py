@@ -1,0 +1,391 @@
+"""nn.Module surface: MinkowskiConvolution(+Transpose), MinkowskiBatchNorm, MinkowskiReLU, cat.
+
+Forward/backward algebra:
+    conv:    out[o] = sum_k in[nbr[o,k]] @ kernel[k]
+             gin[i] = sum_k gout[nbr_T[i,k]] @ kernel[k]^T ;  gkernel[k] = in[I_k]^T @ gout[O_k]
+    convT:   forward strided map with in/out swapped and the same kernel index.
+The products run in libb2s (include/b2s.h: b2s_conv_table / b2s_conv_pairs / b2s_conv_wgrad).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .sparse_tensor import SparseTensor
+
+
+# ------------------------------------------------------------------------------------------
+# autograd functions (raw feature matrices + cached kernel maps)
+# ------------------------------------------------------------------------------------------
+class _ConvSame(torch.autograd.Function):
+    """Stride-1 odd-size convolution on one coordinate map: symmetric kernel map."""
+
+    @staticmethod
+    def forward(ctx, feats, kernel, kmap):
+        feats = feats.contiguous()
+        K, cin, cout = kernel.shape
+        out = ops.conv_table(feats, kernel, kmap.nbr, kmap.n_out, K, cin, cout)
+        ctx.save_for_backward(feats, kernel)
+        ctx.kmap = kmap
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        feats, kernel = ctx.saved_tensors
+        kmap = ctx.kmap
+        K, cin, cout = kernel.shape
+        gout = gout.contiguous()
+        gin = gk = None
+        if ctx.needs_input_grad[0]:
+            # nbr[i, K-1-k] = o  <=>  nbr[o, k] = i: reuse the table with reversed, transposed weights
+            gin = ops.conv_table(gout, kernel, kmap.nbr, kmap.n_in, K, cout, cin, w_transposed=True, k_reversed=True)
+        if ctx.needs_input_grad[1]:
+            pin, pout, koff, maxp = kmap.pairs()
+            gk = ops.conv_wgrad(feats, gout, pin, pout, koff, K, cin, cout, maxp)
+        return gin, gk, None
+
+
+class _ConvDown(torch.autograd.Function):
+    """kernel_size == stride (2) convolution: fine -> coarse, table nbr[coarse, 8] of fine rows."""
+
+    @staticmethod
+    def forward(ctx, feats, kernel, kmap):
+        feats = feats.contiguous()
+        K, cin, cout = kernel.shape
+        out = ops.conv_table(feats, kernel, kmap.nbr, kmap.n_out, K, cin, cout)
+        ctx.save_for_backward(feats, kernel)
+        ctx.kmap = kmap
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        feats, kernel = ctx.saved_tensors
+        kmap = ctx.kmap
+        K, cin, cout = kernel.shape
+        gout = gout.contiguous()
+        pin, pout, koff, maxp = kmap.pairs()
+        gin = gk = None
+        if ctx.needs_input_grad[0]:
+            # every fine row has exactly one (coarse row, offset): plain store, no accumulation
+            gin = ops.conv_pairs(gout, kernel, pout, pin, koff, kmap.n_in, K, cout, cin, maxp, w_transposed=True)
+        if ctx.needs_input_grad[1]:
+            gk = ops.conv_wgrad(feats, gout, pin, pout, koff, K, cin, cout, maxp)
+        return gin, gk, None
+
+
+class _ConvUp(torch.autograd.Function):
+    """Transposed kernel_size == stride (2) convolution: coarse -> fine on the existing fine map.
+
+    kmap is the FORWARD strided map (fine -> coarse); it is used with in/out swapped.
+    """
+
+    @staticmethod
+    def forward(ctx, feats, kernel, kmap):
+        feats = feats.contiguous()
+        K, cin, cout = kernel.shape
+        pin, pout, koff, maxp = kmap.pairs()
+        out = ops.conv_pairs(feats, kernel, pout, pin, koff, kmap.n_in, K, cin, cout, maxp)
+        ctx.save_for_backward(feats, kernel)
+        ctx.kmap = kmap
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        feats, kernel = ctx.saved_tensors
+        kmap = ctx.kmap
+        K, cin, cout = kernel.shape
+        gout = gout.contiguous()
+        gin = gk = None
+        if ctx.needs_input_grad[0]:
+            gin = ops.conv_table(gout, kernel, kmap.nbr, kmap.n_out, K, cout, cin, w_transposed=True)
+        if ctx.needs_input_grad[1]:
+            pin, pout, koff, maxp = kmap.pairs()
+            gk = ops.conv_wgrad(feats, gout, pout, pin, koff, K, cin, cout, maxp)
+        return gin, gk, None
+
+
+class _Conv1x1(torch.autograd.Function):
+    """kernel_size 1, stride 1: dense [M,Cin] @ [Cin,Cout] through the same implicit-GEMM kernel."""
+
+    @staticmethod
+    def forward(ctx, feats, kernel):
+        feats = feats.contiguous()
+        cin, cout = kernel.shape
+        out = ops.conv_table(feats, kernel, None, feats.size(0), 1, cin, cout)
+        ctx.save_for_backward(feats, kernel)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        feats, kernel = ctx.saved_tensors
+        cin, cout = kernel.shape
+        gout = gout.contiguous()
+        gin = gk = None
+        if ctx.needs_input_grad[0]:
+            gin = ops.conv_table(gout, kernel, None, feats.size(0), 1, cout, cin, w_transposed=True)
+        if ctx.needs_input_grad[1]:
+            gk = feats.t().mm(gout)  # plain library GEMM for the 1x1 weight gradient
+        return gin, gk
+
+
+# ------------------------------------------------------------------------------------------
+# modules
+# ------------------------------------------------------------------------------------------
+def _scalar(v, name):
+    if isinstance(v, (list, tuple)):
+        if len(set(v)) != 1:
+            raise NotImplementedError("anisotropic %s is not supported" % name)
+        v = v[0]
+    return int(v)
+
+
+class _ConvBase(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, is_transpose=False, expand_coordinates=False, dimension=None, **_unused):
+        super().__init__()
+        if dimension != 3:
+            raise NotImplementedError("only dimension=3 is supported (every minsu3d call site uses 3)")
+        if kernel_generator is not None or expand_coordinates:
+            raise NotImplementedError("custom kernel generators / expand_coordinates are not supported")
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _scalar(kernel_size, "kernel_size")
+        self.stride = _scalar(stride, "stride")
+        self.dilation = _scalar(dilation, "dilation")
+        self.is_transpose = is_transpose
+        self.dimension = dimension
+        if self.dilation != 1:
+            raise NotImplementedError("dilation != 1 is not used by minsu3d and not supported")
+        self.kernel_volume = self.kernel_size ** 3
+        self.use_mm = self.kernel_volume == 1 and self.stride == 1
+        if self.use_mm:
+            shape = (in_channels, out_channels)
+        else:
+            shape = (self.kernel_volume, in_channels, out_channels)
+        self.kernel = nn.Parameter(torch.empty(shape, dtype=torch.float32))
+        self.bias = nn.Parameter(torch.empty(1, out_channels, dtype=torch.float32)) if bias else None
+        self.reset_parameters(is_transpose)
+
+    def reset_parameters(self, is_transpose=False):
+        with torch.no_grad():
+            n = (self.out_channels if is_transpose else self.in_channels) * self.kernel_volume
+            stdv = 1.0 / math.sqrt(n)
+            self.kernel.uniform_(-stdv, stdv)
+            if self.bias is not None:
+                self.bias.uniform_(-stdv, stdv)
+
+    def _finish(self, x, feats, key):
+        if self.bias is not None:
+            feats = feats + self.bias
+        return SparseTensor(feats, coordinate_map_key=key, coordinate_manager=x.coordinate_manager)
+
+    def extra_repr(self):
+        return "in=%d, out=%d, kernel_size=%d, stride=%d" % (self.in_channels, self.out_channels,
+                                                              self.kernel_size, self.stride)
+
+
+class MinkowskiConvolution(_ConvBase):
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, expand_coordinates=False, convolution_mode=None, dimension=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride, dilation, bias, kernel_generator,
+                         False, expand_coordinates, dimension)
+
+    def forward(self, x):
+        mgr, key = x.coordinate_manager, x.coordinate_map_key
+        if self.use_mm:
+            return self._finish(x, _Conv1x1.apply(x.F, self.kernel), key)
+        if self.stride == 1:
+            if self.kernel_size % 2 != 1:
+                raise NotImplementedError("stride-1 convolutions need an odd kernel size")
+            kmap = mgr.kernel_map(key, key, self.kernel_size)
+            return self._finish(x, _ConvSame.apply(x.F, self.kernel, kmap), key)
+        if self.stride != self.kernel_size:
+            raise NotImplementedError("strided convolution is supported for kernel_size == stride (2/2)")
+        out_key = mgr.stride_key(key, self.stride)
+        kmap = mgr.kernel_map(key, out_key, self.kernel_size)
+        return self._finish(x, _ConvDown.apply(x.F, self.kernel, kmap), out_key)
+
+
+class MinkowskiConvolutionTranspose(_ConvBase):
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, expand_coordinates=False, convolution_mode=None, dimension=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride, dilation, bias, kernel_generator,
+                         True, expand_coordinates, dimension)
+
+    def forward(self, x):
+        mgr, key = x.coordinate_manager, x.coordinate_map_key
+        if self.use_mm:
+            return self._finish(x, _Conv1x1.apply(x.F, self.kernel), key)
+        if self.stride != self.kernel_size or key.stride % self.stride != 0:
+            raise NotImplementedError("transposed convolution is supported for kernel_size == stride (2/2)")
+        fine_key = mgr.existing_key(key.stride // self.stride)  # the encoder's map (appendix A.6)
+        kmap = mgr.kernel_map(fine_key, key, self.kernel_size)
+        return self._finish(x, _ConvUp.apply(x.F, self.kernel, kmap), fine_key)
+
+
+# ---- normalisation / activation -------------------------------------------------------------
+class _BNReLU(torch.autograd.Function):
+    """y = relu?(batch_norm(x)) with libb2s kernels: stats pass + fused apply, fused backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, relu):
+        x = x.contiguous()
+        n = x.size(0)
+        if training:
+            mean, var = ops.bn_stats(x)
+            if running_mean is not None:
+                with torch.no_grad():
+                    unbiased = var * (float(n) / max(n - 1, 1))
+                    running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+                    running_var.mul_(1 - momentum).add_(unbiased, alpha=momentum)
+        else:
+            mean, var = running_mean, running_var
+        rstd = torch.rsqrt(var + eps)
+        y = ops.bn_apply(x, mean, rstd, weight, bias, relu)
+        ctx.save_for_backward(x, y if relu else x, mean, rstd, weight)
+        ctx.relu = relu
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, rstd, weight = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.bn_backward(x, y, dy.contiguous(), mean, rstd, weight, ctx.relu, ctx.training)
+        return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+class MinkowskiBatchNorm(nn.Module):
+    """nn.BatchNorm1d on the feature matrix; child module is named `bn` like MinkowskiEngine's."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+        super().__init__()
+        self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
+                                 track_running_stats=track_running_stats)
+
+    def _features(self, feats, relu):
+        bn = self.bn
+        c = feats.size(1)
+        use_batch = bn.training or not bn.track_running_stats
+        if not bn.affine or c % 4 != 0 or feats.size(0) == 0 or (bn.momentum is None and use_batch):
+            y = bn(feats)
+            return torch.relu(y) if relu else y
+        if use_batch and bn.track_running_stats:
+            bn.num_batches_tracked += 1
+        return _BNReLU.apply(feats, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch,
+                             bn.momentum, bn.eps, relu)
+
+    def forward(self, x):
+        out = x._like(None)
+        out._pending_bn = (self, x.F)  # materialised on first access; fused with a following ReLU
+        return _LazyBN.wrap(out)
+
+    def __repr__(self):
+        return "MinkowskiBatchNorm(%d, eps=%g, momentum=%s)" % (self.bn.num_features, self.bn.eps, self.bn.momentum)
+
+
+class _LazyBN:
+    """Defers BN so that BN -> ReLU (every use in minsu3d: common.py:13-14,35-39,67-68,75-76;
+    backbone.py:16-17) runs as one fused apply kernel instead of two passes."""
+
+    @staticmethod
+    def wrap(st):
+        st.__class__ = _PendingSparseTensor
+        return st
+
+
+class _PendingSparseTensor(SparseTensor):
+    def _materialise(self, relu):
+        mod, feats = self._pending_bn
+        self._pending_bn = None
+        self._F = mod._features(feats, relu)
+        self.__class__ = SparseTensor
+        return self
+
+    @property
+    def F(self):
+        return self._materialise(False)._F
+
+    @property
+    def features(self):
+        return self._materialise(False)._F
+
+    @features.setter
+    def features(self, value):
+        self._pending_bn = None
+        self._F = value
+        self.__class__ = SparseTensor
+
+    @property
+    def device(self):
+        return self._pending_bn[1].device
+
+    @property
+    def dtype(self):
+        return self._pending_bn[1].dtype
+
+    @property
+    def shape(self):
+        return self._pending_bn[1].shape
+
+    def size(self, *a):
+        return self._pending_bn[1].size(*a)
+
+    def __len__(self):
+        return self._pending_bn[1].size(0)
+
+    def __add__(self, other):
+        return self._materialise(False).__add__(other)
+
+    def __iadd__(self, other):
+        return self._materialise(False).__iadd__(other)
+
+    def __sub__(self, other):
+        return self._materialise(False).__sub__(other)
+
+    def __mul__(self, other):
+        return self._materialise(False).__mul__(other)
+
+
+class MinkowskiReLU(nn.Module):
+    def __init__(self, inplace=False):
+        super().__init__()
+        self.inplace = inplace
+
+    def forward(self, x):
+        if isinstance(x, _PendingSparseTensor):
+            return x._materialise(True)
+        return x._like(torch.relu(x.F))
+
+    def __repr__(self):
+        return "MinkowskiReLU()"
+
+
+class MinkowskiLinear(nn.Module):
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.linear = nn.Linear(in_features, out_features, bias=bias)
+
+    def forward(self, x):
+        return x._like(self.linear(x.F))
+
+
+class MinkowskiGlobalAvgPooling(nn.Module):
+    """Per-batch-index mean of the features (unused by minsu3d; thin alias over the S3 kernel)."""
+
+    def forward(self, x):
+        from ..common_ops.functions.softgroup_ops import global_avg_pool
+        idx = x.C[:, 0].long()
+        order = torch.argsort(idx, stable=True)
+        offsets = torch.cumsum(torch.bincount(idx + 1), dim=0).int()
+        return global_avg_pool(x.F[order].contiguous(), offsets)
+
+
+def cat(*sparse_tensors):
+    """Channel concatenation of tensors on the same coordinate map (common.py:93)."""
+    if len(sparse_tensors) == 1 and isinstance(sparse_tensors[0], (list, tuple)):
+        sparse_tensors = tuple(sparse_tensors[0])
+    first = sparse_tensors[0]
+    for s in sparse_tensors[1:]:
+        first._check_same_map(s)
+    return first._like(torch.cat([s.F for s in sparse_tensors], dim=1))

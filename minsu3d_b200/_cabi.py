@@ -1,0 +1,122 @@
+"""ctypes binding of libb2s.so (include/b2s.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, the error is
+raised.  torch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb2s.so")
+
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_i32 = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_f32 = ctypes.c_float
+c_size = ctypes.c_size_t
+
+# name -> (restype, argtypes)
+_P = c_void_p
+_SIGNATURES = {
+    "b2s_version": (c_i32, []),
+    "b2s_last_error_string": (ctypes.c_char_p, []),
+    "b2s_hash_capacity": (c_i64, [c_i64]),
+    "b2s_coord_unique_ws_bytes": (c_size, [c_i64]),
+    "b2s_coord_unique": (c_i32, [_P, c_i64, c_i32, _P, _P, c_i64, _P, _P, _P, _P, _P, c_size, _P]),
+    "b2s_kernel_map": (c_i32, [_P, c_i64, c_i32, c_i32, _P, _P, c_i64, _P, _P]),
+    "b2s_pairs_ws_bytes": (c_size, [c_i64, c_i32]),
+    "b2s_pairs_from_nbr": (c_i32, [_P, c_i64, c_i32, c_i64, _P, _P, _P, _P, _P, c_size, _P]),
+    "b2s_conv_table": (c_i32, [_P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P]),
+    "b2s_conv_pairs": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, _P]),
+    "b2s_conv_wgrad": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i64, c_i32, _P]),
+    "b2s_bn_ws_bytes": (c_size, [c_i64, c_i32]),
+    "b2s_bn_stats": (c_i32, [_P, c_i64, c_i32, c_f32, _P, _P, _P, c_size, _P]),
+    "b2s_bn_apply": (c_i32, [_P, c_i64, c_i32, _P, _P, _P, _P, c_i32, _P, _P]),
+    "b2s_bn_backward": (c_i32, [_P, _P, _P, c_i64, c_i32, _P, _P, _P, c_i32, c_i32, _P, _P, _P, _P, c_size, _P]),
+    "b2s_gather_rows": (c_i32, [_P, _P, c_i64, c_i32, _P, _P]),
+    "b2s_scatter_add_rows": (c_i32, [_P, _P, c_i64, c_i32, _P, _P]),
+    "b2s_ballquery_ws_bytes": (c_size, [c_i64]),
+    "b2s_ballquery_count": (c_i32, [_P, _P, _P, c_i64, c_i32, c_f32, _P, _P, _P, c_size, _P]),
+    "b2s_ballquery_fill": (c_i32, [_P, _P, _P, c_i64, c_i32, c_f32, _P, _P, _P, c_size, _P]),
+    "b2s_cluster_ws_bytes": (c_size, [c_i64]),
+    "b2s_cluster_label": (c_i32, [_P, _P, _P, c_i64, _P, _P, c_size, _P]),
+    "b2s_cluster_select": (c_i32, [_P, _P, c_i64, c_i32, c_i32, c_f32, _P, c_i32, _P, _P, _P, _P, c_size, _P]),
+    "b2s_cluster_order": (c_i32, [_P, _P, _P, _P, c_i64, _P, _P, c_i32, _P, _P, c_size, _P]),
+    "b2s_cluster_centers": (c_i32, [_P, _P, c_i32, _P, _P, _P, _P, _P]),
+    "b2s_ha_assign": (c_i32, [_P, c_i32, _P, _P, c_i32, _P, _P, _P]),
+    "b2s_ha_concat_ws_bytes": (c_size, [c_i32, c_i32]),
+    "b2s_ha_concat": (c_i32, [_P, _P, c_i32, _P, _P, c_i32, _P, _P, _P, _P, c_size, _P]),
+    "b2s_sec_mean": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
+    "b2s_sec_min": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
+    "b2s_sec_max": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
+    "b2s_roipool_fp": (c_i32, [_P, _P, _P, _P, c_i32, c_i32, _P]),
+    "b2s_roipool_bp": (c_i32, [_P, _P, _P, _P, c_i32, c_i32, _P]),
+    "b2s_global_avg_pool_fp": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
+    "b2s_global_avg_pool_bp": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
+    "b2s_get_iou": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, _P]),
+    "b2s_get_mask_label": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_f32, _P, _P, _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """Load libb2s.so once; raise loudly when it is absent (no CPU / eager fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libb2s.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python minsu3d_b200/csrc/build.py`. There is no CPU fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().b2s_last_error_string().decode()
+        raise RuntimeError("libb2s %s failed with code %d: %s" % (what, rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_WS = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per (device, stream); stream-ordered reuse is safe."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream())
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise ValueError("expected a CUDA tensor (libb2s has no CPU path)")
+
+
+def require(cond, msg):
+    if not cond:
+        raise ValueError(msg)

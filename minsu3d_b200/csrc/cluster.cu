@@ -1,0 +1,639 @@
+// C2 / C3 / C4: BFS clustering on the GPU, bit-exact with the reference's sequential CPU BFS.
+//
+// Reference: minsu3d/common_ops/src/bfs_cluster/bfs_cluster.cpp:28-187 (pg_/sg_ variants) and
+// hierarchical_aggregation/hierarchical_aggregation.cpp:8-97, .cu:20-91.
+//
+// The reference visits seeds in ascending index and grows each cluster by a FIFO BFS over the
+// (possibly asymmetric, because of the 1000-neighbour cap) ball-query lists.  Two facts make a
+// parallel restatement exact:
+//   (1) membership: v belongs to the cluster of m(v) = the lowest index that reaches v along
+//       directed edges (proof in DESIGN.md).  m is the fixpoint of  m(w) = min(m(w), m(u)) over
+//       edges u->w; pointer jumping m(v) = m(m(v)) is valid because reachability is transitive.
+//   (2) order: BFS visit order is level-synchronous; inside a level nodes are ordered by
+//       (queue position of the first frontier node listing them, position in that node's list).
+// Both run as persistent cooperative kernels with a device-wide barrier: no host round trip
+// per level (the reference copies the whole CSR to the host and runs single-threaded).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace b2s {
+
+// ---- device-wide barrier for cooperative (co-resident) grids --------------------------------
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned gen = *((volatile unsigned*)(bar + 1));
+    if (atomicAdd(bar, 1u) == nblocks - 1) {
+      *((volatile unsigned*)bar) = 0;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      while (*((volatile unsigned*)(bar + 1)) == gen) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+constexpr int CL_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------
+// (1) membership labels
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CL_THREADS)
+    cc_label_kernel(const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ start_len,
+                    const int16_t* __restrict__ labels, int n, int32_t* comp, unsigned* bar,
+                    int* flags) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nthreads = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = gtid >> 5, nwarps = nthreads >> 5;
+  for (int v = gtid; v < n; v += nthreads) comp[v] = v;
+  grid_sync(bar, gridDim.x);
+  int it = 0;
+  while (true) {
+    int* flag = flags + (it & 1);
+    for (int u = gwarp; u < n; u += nwarps) {
+      int cu = __ldcg(comp + u);
+      int s = __ldg(start_len + 2 * u), l = __ldg(start_len + 2 * u + 1);
+      int lab = labels ? labels[u] : 0;
+      bool ch = false;
+      for (int e = lane; e < l; e += 32) {
+        int w = __ldg(nbr_idx + s + e);
+        if (labels && labels[w] != lab) continue;
+        if (cu < __ldcg(comp + w)) {
+          int old = atomicMin(comp + w, cu);
+          ch |= (cu < old);
+        }
+      }
+      if (__any_sync(0xffffffffu, ch) && lane == 0) *flag = 1;
+    }
+    grid_sync(bar, gridDim.x);
+    if (gtid == 0) flags[(it + 1) & 1] = 0;
+    for (int v = gtid; v < n; v += nthreads) {
+      int c = __ldcg(comp + v);
+      int cc = __ldcg(comp + c);
+      if (cc < c) {
+        atomicMin(comp + v, cc);
+        *flag = 1;
+      }
+    }
+    grid_sync(bar, gridDim.x);
+    int changed = *((volatile int*)flag);
+    if (!changed) break;
+    ++it;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// selection
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cl_hist_kernel(const int32_t* __restrict__ comp, int n,
+                                                      int32_t* __restrict__ size) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) atomicAdd(size + comp[v], 1);
+}
+
+__global__ void __launch_bounds__(256)
+    cl_keep_kernel(const int32_t* __restrict__ comp, const int16_t* __restrict__ labels, int n,
+                   const int32_t* __restrict__ size, int mode, int thr_i, float thr_f,
+                   const float* __restrict__ point_num_avg, int group, int32_t* __restrict__ flag,
+                   int32_t* __restrict__ ksize) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  bool keep = false;
+  int sz = size[v];
+  if (comp[v] == v) {
+    if (mode == 0) keep = sz >= thr_i;
+    else if (mode == 1) keep = (float)sz >= thr_f;  // bfs_cluster.cpp:116-121 (int compared as float)
+    else {
+      // hierarchical_aggregation.cpp:58-74: double literal x float mean, rounded into float
+      float mean = point_num_avg[labels[v]];
+      float low = (float)(0.05 * (double)mean);
+      float high = (float)(0.3 * (double)mean);
+      float fs = (float)sz;
+      bool frag = fs < high;
+      if (group == 1) keep = frag && fs >= low;  // kept fragments
+      else if (group == 2) keep = !frag;         // primary
+      else keep = frag;                          // every fragment
+    }
+  }
+  flag[v] = keep ? 1 : 0;
+  ksize[v] = keep ? sz : 0;
+}
+
+__global__ void __launch_bounds__(256)
+    cl_emit_kernel(int n, const int32_t* __restrict__ flag, const int32_t* __restrict__ ksize,
+                   const int32_t* __restrict__ cidx, const int32_t* __restrict__ coff,
+                   int32_t* __restrict__ cluster_offsets, int32_t* __restrict__ seeds,
+                   int32_t* __restrict__ d_count) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  if (flag[v]) {
+    seeds[cidx[v]] = v;
+    cluster_offsets[cidx[v]] = coff[v];
+  }
+  if (v == n - 1) {
+    int nc = cidx[v] + flag[v], tot = coff[v] + ksize[v];
+    cluster_offsets[nc] = tot;
+    d_count[0] = nc;
+    d_count[1] = tot;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// (2) BFS visit order, all kept clusters at once
+// ------------------------------------------------------------------------------------------
+struct OrderArgs {
+  const int32_t* nbr_idx;
+  const int32_t* start_len;
+  const int16_t* labels;
+  const int32_t* comp;
+  const int32_t* cluster_offsets;
+  const int32_t* seeds;
+  int32_t* cluster_idxs;
+  int32_t *cid, *seedcid, *pos, *parent, *F0, *F1, *cnt, *base, *fstart, *fnext, *filled, *blocksum;
+  unsigned* bar;
+  int n, n_cluster;
+};
+
+__device__ __forceinline__ int block_sum(int v, int* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+  for (int i = 0; i < CL_THREADS / 32; ++i) t += s_red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(CL_THREADS) bfs_order_kernel(OrderArgs a) {
+  __shared__ int s_red[CL_THREADS / 32];
+  __shared__ int s_scan[CL_THREADS / 32];
+  const int G = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  const int gtid = blockIdx.x * blockDim.x + tid, nthreads = G * blockDim.x;
+  const int gwarp = gtid >> 5, nwarps = nthreads >> 5;
+  const int n = a.n, nC = a.n_cluster;
+
+  for (int v = gtid; v < n; v += nthreads) {
+    a.seedcid[v] = -1;
+    a.pos[v] = -1;
+    a.parent[v] = 0x7fffffff;
+  }
+  grid_sync(a.bar, G);
+  for (int c = gtid; c < nC; c += nthreads) {
+    int s = a.seeds[c];
+    a.seedcid[s] = c;
+    int off = a.cluster_offsets[c];
+    a.F0[c] = s;
+    a.pos[s] = off;
+    a.cluster_idxs[2 * off] = c;
+    a.cluster_idxs[2 * off + 1] = s;
+    a.filled[c] = 1;
+    a.fstart[c] = c;
+  }
+  if (gtid == 0) a.fstart[nC] = nC;
+  grid_sync(a.bar, G);
+  for (int v = gtid; v < n; v += nthreads) a.cid[v] = a.seedcid[a.comp[v]];
+  grid_sync(a.bar, G);
+
+  int32_t* F = a.F0;
+  int32_t* Fn = a.F1;
+  int fsize = nC;
+  while (fsize > 0) {
+    // ---- A: every frontier node claims its unvisited neighbours (lowest queue position wins)
+    for (int f = gwarp; f < fsize; f += nwarps) {
+      int u = F[f];
+      int cu = a.cid[u];
+      int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
+      int lab = a.labels ? a.labels[u] : 0;
+      for (int e = lane; e < l; e += 32) {
+        int w = __ldg(a.nbr_idx + s + e);
+        if (a.cid[w] != cu) continue;
+        if (a.labels && a.labels[w] != lab) continue;
+        if (__ldcg(a.pos + w) >= 0) continue;
+        atomicMin(a.parent + w, f);
+      }
+    }
+    grid_sync(a.bar, G);
+    // ---- B: children per frontier node; frontier split into contiguous per-block ranges
+    const int per = (fsize + G - 1) / G;
+    const int fb = min(fsize, (int)blockIdx.x * per), fe = min(fsize, fb + per);
+    int mysum = 0;
+    for (int f = fb + wib; f < fe; f += CL_THREADS / 32) {
+      int u = F[f];
+      int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
+      int c = 0;
+      for (int e0 = 0; e0 < l; e0 += 32) {
+        int e = e0 + lane;
+        bool child = false;
+        if (e < l) {
+          int w = __ldg(a.nbr_idx + s + e);
+          child = (__ldcg(a.parent + w) == f) && (__ldcg(a.pos + w) < 0);
+        }
+        c += __popc(__ballot_sync(0xffffffffu, child));
+      }
+      if (lane == 0) {
+        a.cnt[f] = c;
+        mysum += c;
+      }
+    }
+    int bsum = block_sum(mysum, s_red);
+    if (tid == 0) a.blocksum[blockIdx.x] = bsum;
+    grid_sync(a.bar, G);
+    // ---- C1: global exclusive scan of cnt -> base (block prefix from blocksum)
+    int pre = 0, tot = 0;
+    for (int b = tid; b < G; b += CL_THREADS) {
+      int v = __ldcg(a.blocksum + b);
+      tot += v;
+      if (b < (int)blockIdx.x) pre += v;
+    }
+    pre = block_sum(pre, s_red);
+    const int total = block_sum(tot, s_red);
+    int running = pre;
+    for (int f0 = fb; f0 < fe; f0 += CL_THREADS) {
+      int f = f0 + tid;
+      int v = (f < fe) ? __ldcg(a.cnt + f) : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      __syncthreads();
+      if (lane == 31) s_scan[wib] = inc;
+      __syncthreads();
+      int woff = 0, ctot = 0;
+      for (int i = 0; i < CL_THREADS / 32; ++i) {
+        int t = s_scan[i];
+        if (i < wib) woff += t;
+        ctot += t;
+      }
+      if (f < fe) a.base[f] = running + woff + inc - v;
+      running += ctot;
+    }
+    if (blockIdx.x == 0 && tid == 0) a.base[fsize] = total;
+    grid_sync(a.bar, G);
+    // ---- C2: emit next frontier + final positions
+    for (int f = fb + wib; f < fe; f += CL_THREADS / 32) {
+      int u = F[f];
+      int c = a.cid[u];
+      int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
+      int cstart = __ldcg(a.base + a.fstart[c]);
+      int pbase = a.cluster_offsets[c] + a.filled[c] - cstart;
+      int j = __ldcg(a.base + f);
+      for (int e0 = 0; e0 < l; e0 += 32) {
+        int e = e0 + lane;
+        bool child = false;
+        int w = 0;
+        if (e < l) {
+          w = __ldg(a.nbr_idx + s + e);
+          child = (__ldcg(a.parent + w) == f) && (__ldcg(a.pos + w) < 0);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, child);
+        if (child) {
+          int jj = j + __popc(m & ((1u << lane) - 1));
+          Fn[jj] = w;
+          int p = pbase + jj;
+          a.pos[w] = p;
+          a.cluster_idxs[2 * p] = c;
+          a.cluster_idxs[2 * p + 1] = w;
+        }
+        j += __popc(m);
+      }
+    }
+    for (int c = gtid; c <= nC; c += nthreads) a.fnext[c] = __ldcg(a.base + a.fstart[c]);
+    grid_sync(a.bar, G);
+    // ---- D: per-cluster bookkeeping (read again only in the next C2)
+    for (int c = gtid; c <= nC; c += nthreads) {
+      int fs = __ldcg(a.fnext + c);
+      if (c < nC) a.filled[c] += __ldcg(a.fnext + c + 1) - fs;
+      a.fstart[c] = fs;
+    }
+    int32_t* t = F;
+    F = Fn;
+    Fn = t;
+    fsize = total;
+    // D's writes are ordered before the next C2 by the barriers of phases A and B
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// HAIS centres: sequential fp32 sums in BFS order (hierarchical_aggregation.cpp:13-37,85-89)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    cluster_centers_kernel(const int32_t* __restrict__ cluster_idxs,
+                           const int32_t* __restrict__ cluster_offsets, int n_cluster,
+                           const float* __restrict__ coords, const int16_t* __restrict__ labels,
+                           const uint8_t* __restrict__ batch_idxs, float* __restrict__ centers) {
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (c >= n_cluster) return;
+  int b = cluster_offsets[c], e = cluster_offsets[c + 1];
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int i0 = b; i0 < e; i0 += 32) {
+    int i = i0 + lane;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (i < e) {
+      int p = cluster_idxs[2 * i + 1];
+      x = coords[3 * p];
+      y = coords[3 * p + 1];
+      z = coords[3 * p + 2];
+    }
+    int m = min(32, e - i0);
+    for (int j = 0; j < m; ++j) {  // strictly sequential adds, same order as the CPU BFS
+      sx = __fadd_rn(sx, __shfl_sync(0xffffffffu, x, j));
+      sy = __fadd_rn(sy, __shfl_sync(0xffffffffu, y, j));
+      sz = __fadd_rn(sz, __shfl_sync(0xffffffffu, z, j));
+    }
+  }
+  if (lane == 0) {
+    float cntf = (float)(e - b);
+    int seed = cluster_idxs[2 * b + 1];
+    centers[5 * c + 0] = __fdiv_rn(sx, cntf);
+    centers[5 * c + 1] = __fdiv_rn(sy, cntf);
+    centers[5 * c + 2] = __fdiv_rn(sz, cntf);
+    centers[5 * c + 3] = (float)labels[seed];
+    centers[5 * c + 4] = (float)batch_idxs[seed];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// HAIS set aggregation (hierarchical_aggregation.cu:20-64): nearest same-class same-scene
+// primary in double precision, strict '<' so the lowest primary index wins ties.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    ha_assign_kernel(const float* __restrict__ fc, int n_frag, const float* __restrict__ pc,
+                     const int32_t* __restrict__ prim_offsets, int n_prim,
+                     const float* __restrict__ radius_avg, int32_t* __restrict__ assign) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frag) return;
+  float fx = fc[5 * f], fy = fc[5 * f + 1], fz = fc[5 * f + 2], fcls = fc[5 * f + 3], fb = fc[5 * f + 4];
+  float nearest = 10000.f;
+  int best = -1;
+  for (int i = 0; i < n_prim; ++i) {
+    if (fabsf(pc[5 * i + 3] - fcls) > 0.1f) continue;
+    if (fabsf(pc[5 * i + 4] - fb) > 0.1f) continue;
+    double dx = (double)(pc[5 * i] - fx), dy = (double)(pc[5 * i + 1] - fy), dz = (double)(pc[5 * i + 2] - fz);
+    float d2 = (float)(dx * dx + dy * dy + dz * dz);
+    if (d2 < nearest) {
+      nearest = d2;
+      best = i;
+    }
+  }
+  int res = -1;
+  if (best >= 0) {
+    int np = prim_offsets[best + 1] - prim_offsets[best];
+    float r_size = (float)(0.01 * (double)sqrtf((float)np));
+    float r_cls = radius_avg[(int)fcls];
+    float r_set = fmaxf(r_size, r_cls);
+    if (nearest < __fmul_rn(r_set, r_set)) res = best;
+  }
+  assign[f] = res;
+}
+
+constexpr int HA_MAX_FRAG = 1024;   // MAX_PER_PRIMARY_ABSORB_FRAGMENT_NUM
+constexpr int HA_MAX_POINT = 8192;  // MAX_PER_PRIMARY_ABSORB_POINT_NUM
+
+// warp per primary; pass 0 counts, pass 1 writes.  Absorbed fragments are taken in ascending
+// fragment index (the reference's order is atomicAdd arrival order, .cu:60).
+__global__ void __launch_bounds__(128)
+    ha_concat_kernel(const int32_t* __restrict__ frag_idxs, const int32_t* __restrict__ frag_offsets,
+                     int n_frag, const int32_t* __restrict__ prim_idxs,
+                     const int32_t* __restrict__ prim_offsets, int n_prim,
+                     const int32_t* __restrict__ assign, int32_t* __restrict__ totals,
+                     const int32_t* __restrict__ out_base, int32_t* __restrict__ out_idxs,
+                     int32_t* __restrict__ out_offsets, int pass) {
+  int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (p >= n_prim) return;
+  int pb = prim_offsets[p], pe = prim_offsets[p + 1];
+  int o = 0;
+  if (pass == 1) {
+    o = out_base[p];
+    for (int i = pb + lane; i < pe; i += 32) {
+      out_idxs[2 * (o + i - pb)] = p;
+      out_idxs[2 * (o + i - pb) + 1] = prim_idxs[2 * i + 1];
+    }
+    o += pe - pb;
+  }
+  int nf = 0, npts = 0;
+  for (int f0 = 0; f0 < n_frag && nf < HA_MAX_FRAG; f0 += 32) {
+    int f = f0 + lane;
+    bool mine = (f < n_frag) && (assign[f] == p);
+    unsigned m = __ballot_sync(0xffffffffu, mine);
+    while (m && nf < HA_MAX_FRAG) {
+      int j = __ffs(m) - 1;
+      m &= m - 1;
+      int ff = f0 + j;
+      int fb = frag_offsets[ff], fe = frag_offsets[ff + 1];
+      int take = min(fe - fb, HA_MAX_POINT - npts);
+      if (pass == 1) {
+        for (int i = lane; i < take; i += 32) {
+          out_idxs[2 * (o + npts + i)] = p;
+          out_idxs[2 * (o + npts + i) + 1] = frag_idxs[2 * (fb + i) + 1];
+        }
+      }
+      npts += take;
+      ++nf;
+    }
+  }
+  if (lane == 0) {
+    if (pass == 0) totals[p] = (pe - pb) + npts;
+    else out_offsets[p + 1] = o + npts;
+  }
+  if (pass == 1 && p == 0 && lane == 0) out_offsets[0] = 0;
+}
+
+static int coop_grid(const void* kernel, int threads, int64_t work_items) {
+  int dev = 0, sms = B2S_SM_COUNT, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+  if (per_sm < 1) per_sm = 1;
+  int g = sms * std::min(per_sm, 2);
+  int64_t want = cdiv(work_items, threads);
+  if (want < 1) want = 1;
+  if (want < g) g = (int)want;
+  return g;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" {
+
+size_t b2s_cluster_ws_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  // order kernel: 11 int arrays of n(+2) + blocksum + barrier; select: 5 arrays + scan
+  return 12 * align_up((size_t)(n + 2) * 4) + scan_ws_bytes(n) + 64 * 1024;
+}
+
+int b2s_cluster_label(const int32_t* nbr_idx, const int32_t* start_len, const int16_t* labels,
+                      int64_t n, int32_t* comp, void* ws, size_t ws_bytes, b2s_stream_t stream) {
+  if (n < 0 || n > 0x3fffffff) {
+    set_error("cluster_label: invalid n");
+    return B2S_E_INVALID;
+  }
+  if (n == 0) return B2S_OK;
+  Workspace w(ws, ws_bytes);
+  unsigned* bar = w.take<unsigned>(64);
+  if (!bar) {
+    set_error("cluster_label: workspace too small");
+    return B2S_E_WORKSPACE;
+  }
+  int* flags = (int*)(bar + 2);
+  cudaMemsetAsync(bar, 0, 64 * 4, stream);
+  int grid = coop_grid((const void*)cc_label_kernel, CL_THREADS, n * 32);
+  int ni = (int)n;
+  void* args[] = {(void*)&nbr_idx, (void*)&start_len, (void*)&labels, (void*)&ni, (void*)&comp, (void*)&bar, (void*)&flags};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)cc_label_kernel, dim3(grid), dim3(CL_THREADS), args, 0, stream);
+  if (e != cudaSuccess) {
+    set_error(cudaGetErrorString(e));
+    return B2S_E_LAUNCH;
+  }
+  return check_launch("cluster_label");
+}
+
+int b2s_cluster_select(const int32_t* comp, const int16_t* labels, int64_t n, int32_t mode,
+                       int32_t thr_i, float thr_f, const float* point_num_avg, int32_t group,
+                       int32_t* cluster_offsets, int32_t* seeds, int32_t* d_count, void* ws,
+                       size_t ws_bytes, b2s_stream_t stream) {
+  if (n < 0 || mode < 0 || mode > 2 || (mode == 2 && (!labels || !point_num_avg))) {
+    set_error("cluster_select: invalid argument");
+    return B2S_E_INVALID;
+  }
+  cudaMemsetAsync(d_count, 0, 8, stream);
+  cudaMemsetAsync(cluster_offsets, 0, 4, stream);
+  if (n == 0) return check_launch("cluster_select(empty)");
+  Workspace w(ws, ws_bytes);
+  int32_t* size = w.take<int32_t>(n);
+  int32_t* flag = w.take<int32_t>(n);
+  int32_t* ksize = w.take<int32_t>(n);
+  int32_t* cidx = w.take<int32_t>(n);
+  int32_t* coff = w.take<int32_t>(n);
+  size_t sbytes = scan_ws_bytes(n);
+  char* sws = w.take<char>(sbytes);
+  if (!sws) {
+    set_error("cluster_select: workspace too small");
+    return B2S_E_WORKSPACE;
+  }
+  int grid = (int)cdiv(n, 256);
+  cudaMemsetAsync(size, 0, (size_t)n * 4, stream);
+  cl_hist_kernel<<<grid, 256, 0, stream>>>(comp, (int)n, size);
+  cl_keep_kernel<<<grid, 256, 0, stream>>>(comp, labels, (int)n, size, mode, thr_i, thr_f, point_num_avg, group, flag, ksize);
+  int rc = exclusive_scan_i32(flag, cidx, n, sws, sbytes, stream);
+  if (rc) return rc;
+  rc = exclusive_scan_i32(ksize, coff, n, sws, sbytes, stream);
+  if (rc) return rc;
+  cl_emit_kernel<<<grid, 256, 0, stream>>>((int)n, flag, ksize, cidx, coff, cluster_offsets, seeds, d_count);
+  return check_launch("cluster_select");
+}
+
+int b2s_cluster_order(const int32_t* nbr_idx, const int32_t* start_len, const int16_t* labels,
+                      const int32_t* comp, int64_t n, const int32_t* cluster_offsets,
+                      const int32_t* seeds, int32_t n_cluster, int32_t* cluster_idxs, void* ws,
+                      size_t ws_bytes, b2s_stream_t stream) {
+  if (n < 0 || n_cluster < 0) {
+    set_error("cluster_order: invalid argument");
+    return B2S_E_INVALID;
+  }
+  if (n == 0 || n_cluster == 0) return B2S_OK;
+  Workspace w(ws, ws_bytes);
+  OrderArgs a;
+  a.nbr_idx = nbr_idx;
+  a.start_len = start_len;
+  a.labels = labels;
+  a.comp = comp;
+  a.cluster_offsets = cluster_offsets;
+  a.seeds = seeds;
+  a.cluster_idxs = cluster_idxs;
+  a.n = (int)n;
+  a.n_cluster = n_cluster;
+  a.bar = w.take<unsigned>(64);
+  a.cid = w.take<int32_t>(n);
+  a.seedcid = w.take<int32_t>(n);
+  a.pos = w.take<int32_t>(n);
+  a.parent = w.take<int32_t>(n);
+  a.F0 = w.take<int32_t>(n);
+  a.F1 = w.take<int32_t>(n);
+  a.cnt = w.take<int32_t>(n + 1);
+  a.base = w.take<int32_t>(n + 1);
+  a.fstart = w.take<int32_t>(n + 2);
+  a.fnext = w.take<int32_t>(n + 2);
+  a.filled = w.take<int32_t>(n + 1);
+  a.blocksum = w.take<int32_t>(4096);
+  if (!a.blocksum) {
+    set_error("cluster_order: workspace too small");
+    return B2S_E_WORKSPACE;
+  }
+  cudaMemsetAsync(a.bar, 0, 64 * 4, stream);
+  int grid = coop_grid((const void*)bfs_order_kernel, CL_THREADS, n * 8);
+  if (grid > 4096) grid = 4096;
+  void* args[] = {(void*)&a};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)bfs_order_kernel, dim3(grid), dim3(CL_THREADS), args, 0, stream);
+  if (e != cudaSuccess) {
+    set_error(cudaGetErrorString(e));
+    return B2S_E_LAUNCH;
+  }
+  return check_launch("cluster_order");
+}
+
+int b2s_cluster_centers(const int32_t* cluster_idxs, const int32_t* cluster_offsets,
+                        int32_t n_cluster, const float* coords, const int16_t* labels,
+                        const uint8_t* batch_idxs, float* centers, b2s_stream_t stream) {
+  if (n_cluster <= 0) return B2S_OK;
+  cluster_centers_kernel<<<(unsigned)cdiv((int64_t)n_cluster * 32, 128), 128, 0, stream>>>(
+      cluster_idxs, cluster_offsets, n_cluster, coords, labels, batch_idxs, centers);
+  return check_launch("cluster_centers");
+}
+
+int b2s_ha_assign(const float* frag_centers, int32_t n_frag, const float* prim_centers,
+                  const int32_t* prim_offsets, int32_t n_prim, const float* radius_avg,
+                  int32_t* assign, b2s_stream_t stream) {
+  if (n_frag <= 0) return B2S_OK;
+  ha_assign_kernel<<<(unsigned)cdiv(n_frag, 256), 256, 0, stream>>>(frag_centers, n_frag, prim_centers,
+                                                                    prim_offsets, n_prim, radius_avg, assign);
+  return check_launch("ha_assign");
+}
+
+size_t b2s_ha_concat_ws_bytes(int32_t n_frag, int32_t n_prim) {
+  (void)n_frag;
+  int64_t n = n_prim > 0 ? n_prim : 1;
+  return 2 * align_up((size_t)n * 4) + scan_ws_bytes(n) + 1024;
+}
+
+int b2s_ha_concat(const int32_t* frag_idxs, const int32_t* frag_offsets, int32_t n_frag,
+                  const int32_t* prim_idxs, const int32_t* prim_offsets, int32_t n_prim,
+                  const int32_t* assign, int32_t* out_idxs, int32_t* out_offsets, void* ws,
+                  size_t ws_bytes, b2s_stream_t stream) {
+  if (n_prim <= 0) {
+    cudaMemsetAsync(out_offsets, 0, 4, stream);
+    return check_launch("ha_concat(empty)");
+  }
+  Workspace w(ws, ws_bytes);
+  int32_t* totals = w.take<int32_t>(n_prim);
+  int32_t* base = w.take<int32_t>(n_prim);
+  size_t sbytes = scan_ws_bytes(n_prim);
+  char* sws = w.take<char>(sbytes);
+  if (!sws) {
+    set_error("ha_concat: workspace too small");
+    return B2S_E_WORKSPACE;
+  }
+  unsigned grid = (unsigned)cdiv((int64_t)n_prim * 32, 128);
+  ha_concat_kernel<<<grid, 128, 0, stream>>>(frag_idxs, frag_offsets, n_frag, prim_idxs, prim_offsets, n_prim,
+                                             assign, totals, base, out_idxs, out_offsets, 0);
+  int rc = exclusive_scan_i32(totals, base, n_prim, sws, sbytes, stream);
+  if (rc) return rc;
+  ha_concat_kernel<<<grid, 128, 0, stream>>>(frag_idxs, frag_offsets, n_frag, prim_idxs, prim_offsets, n_prim,
+                                             assign, totals, base, out_idxs, out_offsets, 1);
+  return check_launch("ha_concat");
+}
+
+}  // extern "C"

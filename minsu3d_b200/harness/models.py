@@ -1,0 +1,482 @@
+"""The reference's callers of the hot path, without the Lightning/Hydra control plane.
+
+These modules exist so that the path can be exercised, parity-tested and benchmarked end to end
+(BASELINE.json configs 1-4).  Structure, parameter names and hyper-parameters follow
+minsu3d/model/module/{common,backbone,tiny_unet}.py and minsu3d/model/{general_model,pointgroup,
+hais,softgroup}.py (state-dict keys match: `backbone.unet.0.kernel`, `...conv_branch.0.bn.weight`),
+but every sparse op goes through minsu3d_b200 (ME shim + common_ops mirror) and the clustering
+stage stays on the device: no `.cpu()` round trips (pointgroup.py:41-63 has six).
+"""
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import MinkowskiEngine as ME
+from .. import ops
+from ..common_ops.functions import common_ops, hais_ops, pointgroup_ops, softgroup_ops
+from . import scenes
+
+
+# ------------------------------------------------------------------------------------------
+# MinkUNet pieces (common.py:21-95, backbone.py:8-43, tiny_unet.py:7-19)
+# ------------------------------------------------------------------------------------------
+class ResidualBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, dimension=3, norm_fn=None):
+        super().__init__()
+        norm_fn = norm_fn or ME.MinkowskiBatchNorm
+        self.downsample = None
+        if in_channels != out_channels:
+            self.downsample = nn.Sequential(
+                ME.MinkowskiConvolution(in_channels, out_channels, kernel_size=1, dimension=dimension))
+        self.conv_branch = nn.Sequential(
+            norm_fn(in_channels), ME.MinkowskiReLU(inplace=True),
+            ME.MinkowskiConvolution(in_channels, out_channels, kernel_size=3, dimension=dimension),
+            norm_fn(out_channels), ME.MinkowskiReLU(inplace=True),
+            ME.MinkowskiConvolution(out_channels, out_channels, kernel_size=3, dimension=dimension))
+
+    def forward(self, x):
+        shortcut = x if self.downsample is None else self.downsample(x)
+        y = self.conv_branch(x)
+        y += shortcut
+        return y
+
+
+class UBlock(nn.Module):
+    def __init__(self, n_planes, norm_fn, block_reps, block):
+        super().__init__()
+        self.nPlanes = list(n_planes)
+        c = self.nPlanes[0]
+        self.blocks = nn.Sequential(OrderedDict(
+            ("block%d" % i, block(c, c, 3, norm_fn)) for i in range(block_reps)))
+        if len(self.nPlanes) > 1:
+            c1 = self.nPlanes[1]
+            self.conv = nn.Sequential(norm_fn(c), ME.MinkowskiReLU(inplace=True),
+                                      ME.MinkowskiConvolution(c, c1, kernel_size=2, stride=2, dimension=3))
+            self.u = UBlock(self.nPlanes[1:], norm_fn, block_reps, block)
+            self.deconv = nn.Sequential(norm_fn(c1), ME.MinkowskiReLU(inplace=True),
+                                        ME.MinkowskiConvolutionTranspose(c1, c, kernel_size=2, stride=2, dimension=3))
+            self.blocks_tail = nn.Sequential(OrderedDict(
+                ("block%d" % i, block(c * (2 - i), c, 3, norm_fn)) for i in range(block_reps)))
+
+    def forward(self, x):
+        out = self.blocks(x)
+        if len(self.nPlanes) > 1:
+            skip = out
+            out = self.deconv(self.u(self.conv(out)))
+            out = self.blocks_tail(ME.cat(skip, out))
+        return out
+
+
+class Backbone(nn.Module):
+    def __init__(self, input_channel, output_channel, block_channels, block_reps, sem_classes):
+        super().__init__()
+        m = output_channel
+        self.unet = nn.Sequential(
+            ME.MinkowskiConvolution(input_channel, m, kernel_size=3, dimension=3),
+            UBlock([m * c for c in block_channels], ME.MinkowskiBatchNorm, block_reps, ResidualBlock),
+            ME.MinkowskiBatchNorm(m), ME.MinkowskiReLU(inplace=True))
+        self.semantic_branch = nn.Sequential(nn.Linear(m, m), nn.BatchNorm1d(m), nn.ReLU(inplace=True),
+                                             nn.Linear(m, sem_classes))
+        self.offset_branch = nn.Sequential(nn.Linear(m, m), nn.BatchNorm1d(m), nn.ReLU(inplace=True),
+                                           nn.Linear(m, 3))
+
+    def forward(self, voxel_features, voxel_coordinates, v2p_map):
+        x = ME.SparseTensor(features=voxel_features, coordinates=voxel_coordinates)
+        unet_out = self.unet(x)
+        point_features = ops.devoxelize(unet_out.features, v2p_map)  # == features[v2p_map], backbone.py:40
+        return {"point_features": point_features,
+                "semantic_scores": self.semantic_branch(point_features),
+                "point_offsets": self.offset_branch(point_features)}
+
+
+class TinyUnet(nn.Module):
+    def __init__(self, channel):
+        super().__init__()
+        self.unet = nn.Sequential(UBlock([channel, 2 * channel], ME.MinkowskiBatchNorm, 2, ResidualBlock),
+                                  ME.MinkowskiBatchNorm(channel), ME.MinkowskiReLU(inplace=True))
+
+    def forward(self, x):
+        return self.unet(x)
+
+
+# ------------------------------------------------------------------------------------------
+# configuration (config/model/{pointgroup,hais,softgroup}.yaml, config/data/scannetv2.yaml)
+# ------------------------------------------------------------------------------------------
+@dataclass
+class Config:
+    model: str = "pointgroup"
+    m: int = 16
+    blocks: List[int] = field(default_factory=lambda: [1, 2, 3, 4, 5, 6, 7])
+    block_reps: int = 2
+    use_color: bool = True
+    use_normal: bool = False
+    classes: int = scenes.NUM_CLASSES
+    ignore_classes: tuple = scenes.IGNORE_CLASSES
+    point_num_avg: List[float] = field(default_factory=lambda: list(scenes.POINT_NUM_AVG))
+    radius_avg: List[float] = field(default_factory=lambda: list(scenes.RADIUS_AVG))
+    fg_thresh: float = 0.75
+    bg_thresh: float = 0.25
+    score_scale: int = 50
+    score_fullscale: int = 14
+    cluster_radius: float = 0.03
+    cluster_meanActive: int = 50
+    cluster_shift_meanActive: int = 300
+    cluster_npoint_thre: int = 50
+    # HAIS
+    using_set_aggr_in_training: bool = False
+    using_set_aggr_in_testing: bool = True
+    use_mask_filter_score_feature: bool = False
+    mask_filter_score_feature_thre: float = 0.5
+    cal_iou_based_on_mask: bool = False
+    # SoftGroup
+    sg_score_thr: float = 0.2
+    sg_radius: float = 0.04
+    sg_mean_active: int = 300
+    sg_npoint_thr: float = 0.05
+    sg_min_npoint: int = 100
+    sg_max_proposal_num: int = 200
+    sg_pos_iou_thr: float = 0.5
+    # where the clustering stage takes its semantic predictions / offsets from:
+    #   "network": the network's own outputs (reference behaviour, pointgroup.py:28-47)
+    #   "gt_noise": ground truth + noise, so that random-init weights still yield proposals
+    proposal_source: str = "network"
+    lr: float = 0.002
+
+    @staticmethod
+    def for_model(name, **kw):
+        base = dict(model=name)
+        if name == "hais":
+            base.update(m=32, score_fullscale=20, lr=0.0015)
+        elif name == "softgroup":
+            base.update(m=32, score_fullscale=20, lr=0.004)
+        base.update(kw)
+        return Config(**base)
+
+
+def clusters_voxelization(clusters_idx, clusters_offset, feats, coords, scale, spatial_shape, rand=None):
+    """general_model.py:152-193.  `rand` ([2,3] tensor) replaces the two torch.rand(3) draws so that
+    parity runs can share them."""
+    device = feats.device
+    batch_idx = clusters_idx[:, 0]
+    c_idxs = clusters_idx[:, 1]
+    feats = feats[c_idxs]
+    cc = coords[c_idxs].contiguous()
+    mean = common_ops.sec_mean(cc, clusters_offset)
+    cc = cc - torch.index_select(mean, 0, batch_idx)
+    cmin = common_ops.sec_min(cc, clusters_offset)
+    cmax = common_ops.sec_max(cc, clusters_offset)
+    cscale = 1 / ((cmax - cmin) / spatial_shape).max(1)[0] - 0.01  # ensures voxel coords < spatial_shape
+    cscale = torch.clamp(cscale, min=None, max=scale)
+    min_xyz, max_xyz = cmin * cscale[:, None], cmax * cscale[:, None]
+    cc = cc * torch.index_select(cscale, 0, batch_idx)[:, None]
+    rng = max_xyz - min_xyz
+    if rand is None:
+        rand = torch.rand(2, 3, device=device)
+    offset = -min_xyz + torch.clamp(spatial_shape - rng - 0.001, min=0) * rand[0]
+    offset = offset + torch.clamp(spatial_shape - rng + 0.001, max=0) * rand[1]
+    cc = cc + torch.index_select(offset, 0, batch_idx)
+    cc = cc.int()
+    batched_xyz = torch.cat((clusters_idx[:, 0].unsqueeze(-1).to(cc.dtype), cc), dim=1)
+    voxel_xyz, voxel_features, _, voxel_point_map = ME.utils.sparse_quantize(
+        batched_xyz, feats, return_index=True, return_inverse=True, device="cuda")
+    return ME.SparseTensor(features=voxel_features, coordinates=voxel_xyz, device=device), voxel_point_map
+
+
+def get_segmented_scores(scores, fg_thresh=1.0, bg_thresh=0.0):
+    """general_model.py:196-213: 1 above fg, 0 below bg, linear in between."""
+    k = 1 / (fg_thresh - bg_thresh)
+    b = bg_thresh / (bg_thresh - fg_thresh)
+    return torch.where(scores > fg_thresh, torch.ones_like(scores),
+                       torch.where(scores < bg_thresh, torch.zeros_like(scores), scores * k + b))
+
+
+def pt_offset_loss(pred_offsets, gt_offsets, valid_mask):
+    """minsu3d/loss/pt_offset_loss.py:12-38."""
+    if valid_mask.count_nonzero() == 0:
+        return 0, 0
+    p, g = pred_offsets[valid_mask], gt_offsets[valid_mask]
+    norm_loss = torch.sum(torch.abs(p - g), dim=-1).mean()
+    eps = torch.finfo(g.dtype).eps
+    dir_loss = -(F.normalize(g, p=2, dim=1, eps=eps) * F.normalize(p, p=2, dim=1, eps=eps)).sum(-1).mean()
+    return norm_loss, dir_loss
+
+
+class GeneralModel(nn.Module):
+    """general_model.py:16-50 without Lightning: backbone forward + semantic/offset losses."""
+
+    def __init__(self, cfg: Config):
+        super().__init__()
+        self.cfg = cfg
+        in_ch = 3 + 3 * cfg.use_color + 3 * cfg.use_normal
+        self.backbone = Backbone(in_ch, cfg.m, cfg.blocks, cfg.block_reps, cfg.classes)
+        self.clustering = True  # current_epoch > prepare_epochs
+
+    def backbone_forward(self, data):
+        return self.backbone(data["voxel_features"], data["voxel_xyz"], data["voxel_point_map"])
+
+    def base_loss(self, data, out):
+        losses = {"semantic_loss": F.cross_entropy(out["semantic_scores"], data["sem_labels"].long(), ignore_index=-1)}
+        gt_offsets = data["instance_center_xyz"] - data["point_xyz"]
+        losses["offset_norm_loss"], losses["offset_dir_loss"] = pt_offset_loss(
+            out["point_offsets"], gt_offsets, data["instance_ids"] != -1)
+        return losses
+
+    # semantic predictions / offsets that drive the clustering stage
+    def _cluster_inputs(self, data, out):
+        if self.cfg.proposal_source == "gt_noise":
+            g = torch.Generator(device=out["semantic_scores"].device)
+            g.manual_seed(1234)
+            sem = data["sem_labels"].long().clamp(min=0)
+            scores = F.one_hot(sem, self.cfg.classes).float() * 8 + torch.randn(
+                out["semantic_scores"].shape, device=sem.device, generator=g)
+            shrink = 0.7 + 0.3 * torch.rand((sem.numel(), 1), device=sem.device, generator=g)
+            offsets = (data["instance_center_xyz"] - data["point_xyz"]) * shrink
+            offsets = torch.where((data["instance_ids"] != -1)[:, None], offsets, torch.zeros_like(offsets))
+            return scores, offsets
+        return out["semantic_scores"], out["point_offsets"]
+
+    def _object_points(self, semantic_preds):
+        mask = torch.ones_like(semantic_preds, dtype=torch.bool)
+        for c in self.cfg.ignore_classes:
+            mask &= semantic_preds != (c - 1)
+        return torch.nonzero(mask).view(-1)
+
+    def training_loss(self, data):
+        out = self(data)
+        losses = self.loss(data, out)
+        return sum(losses.values()), losses, out
+
+
+class PointGroup(GeneralModel):
+    """pointgroup.py:12-109."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.score_net = TinyUnet(cfg.m)
+        self.score_branch = nn.Linear(cfg.m, 1)
+
+    def forward(self, data, rand=None):
+        cfg = self.cfg
+        out = self.backbone_forward(data)
+        if not self.clustering:
+            return out
+        scores, offsets = self._cluster_inputs(data, out)
+        semantic_preds = scores.argmax(1).to(torch.int16)
+        object_idxs = self._object_points(semantic_preds)
+        batch_idxs_ = data["vert_batch_ids"][object_idxs]
+        batch_offsets_ = torch.cumsum(torch.bincount(batch_idxs_ + 1), dim=0).int()
+        coords_ = data["point_xyz"][object_idxs]
+        sem_ = semantic_preds[object_idxs].contiguous()
+        sets = []
+        for xyz, mean_active in ((coords_.contiguous(), cfg.cluster_meanActive),
+                                 ((coords_ + offsets.detach()[object_idxs]).contiguous(), cfg.cluster_shift_meanActive)):
+            idx, start_len = common_ops.ballquery_batch_p(xyz, batch_idxs_, batch_offsets_, cfg.cluster_radius, mean_active)
+            p_idx, p_off = pointgroup_ops.pg_bfs_cluster(sem_, idx, start_len, cfg.cluster_npoint_thre)
+            p_idx = p_idx.long()
+            p_idx[:, 1] = object_idxs[p_idx[:, 1]]
+            sets.append((p_idx, p_off))
+        (p_idx, p_off), (s_idx, s_off) = sets  # unshifted first, shifted appended (pointgroup.py:70-73)
+        s_idx[:, 0] += p_off.size(0) - 1
+        proposals_idx = torch.cat((p_idx, s_idx), dim=0)
+        proposals_offset = torch.cat((p_off, s_off[1:] + p_off[-1]))
+        out["proposal_scores"] = None
+        if proposals_offset.numel() > 1:
+            vox, p2v = clusters_voxelization(proposals_idx, proposals_offset, out["point_features"], data["point_xyz"],
+                                             cfg.score_scale, cfg.score_fullscale, rand)
+            score_feats = self.score_net(vox)
+            pt_score_feats = ops.devoxelize(score_feats.features, p2v)
+            proposals_score_feats = common_ops.roipool(pt_score_feats, proposals_offset)
+            out["proposal_scores"] = (self.score_branch(proposals_score_feats), proposals_idx, proposals_offset)
+        return out
+
+    def loss(self, data, out):
+        losses = self.base_loss(data, out)
+        if self.clustering and out.get("proposal_scores") is not None:
+            scores, proposals_idx, proposals_offset = out["proposal_scores"]
+            ious = common_ops.get_iou(proposals_idx[:, 1].int().contiguous(), proposals_offset,
+                                      data["instance_ids"], data["instance_num_point"])
+            gt_scores = get_segmented_scores(ious.max(1)[0], self.cfg.fg_thresh, self.cfg.bg_thresh)
+            losses["score_loss"] = F.binary_cross_entropy_with_logits(scores.view(-1), gt_scores)
+        return losses
+
+
+class HAIS(GeneralModel):
+    """hais.py:12-127."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        m = cfg.m
+        self.tiny_unet = TinyUnet(m)
+        self.score_branch = nn.Linear(m, 1)
+        self.mask_branch = nn.Sequential(nn.Linear(m, m), nn.ReLU(inplace=True), nn.Linear(m, 1))
+
+    def forward(self, data, rand=None):
+        cfg = self.cfg
+        out = self.backbone_forward(data)
+        if not self.clustering:
+            return out
+        scores, offsets = self._cluster_inputs(data, out)
+        semantic_preds = scores.argmax(1).to(torch.int16)
+        object_idxs = self._object_points(semantic_preds)
+        batch_idxs_ = data["vert_batch_ids"][object_idxs]
+        batch_offsets_ = torch.cumsum(torch.bincount(batch_idxs_ + 1), dim=0).int()
+        offset_coords_ = (data["point_xyz"][object_idxs] + offsets.detach()[object_idxs]).contiguous()
+        idx, start_len = common_ops.ballquery_batch_p(offset_coords_, batch_idxs_, batch_offsets_, cfg.cluster_radius,
+                                                      cfg.cluster_shift_meanActive)
+        set_aggr = cfg.using_set_aggr_in_training if self.training else cfg.using_set_aggr_in_testing
+        proposals_idx, proposals_offset = hais_ops.hierarchical_aggregation(
+            semantic_preds[object_idxs].contiguous(), offset_coords_, idx, start_len, batch_idxs_.contiguous(),
+            set_aggr, cfg.point_num_avg, cfg.radius_avg, -1)
+        proposals_idx = proposals_idx.long()
+        proposals_idx[:, 1] = object_idxs[proposals_idx[:, 1]]
+        out["proposal_scores"] = None
+        if proposals_offset.numel() > 1:
+            vox, p2v = clusters_voxelization(proposals_idx, proposals_offset, out["point_features"], data["point_xyz"],
+                                             cfg.score_scale, cfg.score_fullscale, rand)
+            inst = self.tiny_unet(vox)
+            score_feats = ops.devoxelize(inst.features, p2v)
+            mask_scores = self.mask_branch(inst.features)[p2v]  # linear first: fewer voxels than points
+            if cfg.use_mask_filter_score_feature:
+                keep = (torch.sigmoid(mask_scores) >= cfg.mask_filter_score_feature_thre).float()
+                score_feats = score_feats * keep
+            score_feats = common_ops.roipool(score_feats.contiguous(), proposals_offset)
+            out["proposal_scores"] = (self.score_branch(score_feats), proposals_idx, proposals_offset, mask_scores)
+        return out
+
+    def loss(self, data, out):
+        losses = self.base_loss(data, out)
+        if self.clustering and out.get("proposal_scores") is not None:
+            scores, proposals_idx, proposals_offset, mask_scores = out["proposal_scores"]
+            sig = torch.sigmoid(mask_scores)
+            pidx = proposals_idx[:, 1].int().contiguous()
+            if self.cfg.cal_iou_based_on_mask:
+                ious = common_ops.get_mask_iou_on_pred(pidx, proposals_offset, data["instance_ids"],
+                                                       data["instance_num_point"], sig.detach().contiguous())
+            else:
+                ious = common_ops.get_mask_iou_on_cluster(pidx, proposals_offset, data["instance_ids"],
+                                                          data["instance_num_point"])
+            mask_label, mask_label_mask = common_ops.get_mask_label(
+                pidx, proposals_offset, data["instance_ids"], data["instance_semantic_cls"],
+                data["instance_num_point"], ious, -1, 0.5)
+            losses["mask_loss"] = F.binary_cross_entropy(sig, mask_label.unsqueeze(1).float(),
+                                                         weight=mask_label_mask.unsqueeze(1).float(), reduction="mean")
+            gt_scores = get_segmented_scores(ious.max(1)[0], self.cfg.fg_thresh, self.cfg.bg_thresh)
+            losses["score_loss"] = F.binary_cross_entropy_with_logits(scores.view(-1), gt_scores)
+        return losses
+
+
+class SoftGroup(GeneralModel):
+    """softgroup.py:11-183."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        m = cfg.m
+        self.instance_classes = cfg.classes - len(cfg.ignore_classes)
+        self.tiny_unet = TinyUnet(m)
+        self.classification_branch = nn.Linear(m, self.instance_classes + 1)
+        self.mask_scoring_branch = nn.Sequential(nn.Linear(m, m), nn.ReLU(inplace=True),
+                                                 nn.Linear(m, self.instance_classes + 1))
+        self.iou_score = nn.Linear(m, self.instance_classes + 1)
+
+    def forward(self, data, rand=None):
+        cfg = self.cfg
+        out = self.backbone_forward(data)
+        if not self.clustering:
+            return out
+        scores, offsets = self._cluster_inputs(data, out)
+        semantic_scores = scores.softmax(dim=-1)
+        offsets = offsets.detach()
+        idx_list, off_list = [], []
+        n_prop, n_pts = 0, 0
+        for class_id in range(cfg.classes):
+            if class_id + 1 in cfg.ignore_classes:
+                continue
+            object_idxs = (semantic_scores[:, class_id] > cfg.sg_score_thr).nonzero().view(-1)
+            if object_idxs.size(0) < cfg.sg_min_npoint:
+                continue
+            batch_idxs_ = data["vert_batch_ids"][object_idxs]
+            batch_offsets_ = torch.cumsum(torch.bincount(batch_idxs_ + 1), dim=0).int()
+            xyz = (data["point_xyz"][object_idxs] + offsets[object_idxs]).contiguous()
+            idx, start_len = common_ops.ballquery_batch_p(xyz, batch_idxs_, batch_offsets_, cfg.sg_radius, cfg.sg_mean_active)
+            p_idx, p_off = softgroup_ops.sg_bfs_cluster(cfg.point_num_avg, idx, start_len, cfg.sg_npoint_thr, class_id)
+            if p_idx.size(0) == 0:
+                continue
+            p_idx = p_idx.long()
+            p_idx[:, 1] = object_idxs[p_idx[:, 1]]
+            p_idx[:, 0] += n_prop
+            idx_list.append(p_idx)
+            off_list.append(p_off[1:] + n_pts if off_list else p_off)
+            n_prop += p_off.numel() - 1
+            n_pts += p_idx.size(0)
+        out["proposals_idx"] = None
+        if not idx_list:
+            return out
+        proposals_idx = torch.cat(idx_list, dim=0)
+        proposals_offset = torch.cat(off_list)
+        if proposals_offset.shape[0] > cfg.sg_max_proposal_num:
+            proposals_offset = proposals_offset[:cfg.sg_max_proposal_num + 1]
+            proposals_idx = proposals_idx[:int(proposals_offset[-1])]
+        out["proposals_idx"], out["proposals_offset"] = proposals_idx, proposals_offset
+        vox, inst_map = clusters_voxelization(proposals_idx, proposals_offset, out["point_features"], data["point_xyz"],
+                                              cfg.score_scale, cfg.score_fullscale, rand)
+        feats = self.tiny_unet(vox)
+        mask_scores = self.mask_scoring_branch(feats.features)
+        out["mask_scores"] = mask_scores[inst_map]
+        out["instance_batch_idxs"] = feats.coordinates[:, 0][inst_map]
+        # global_pool (softgroup.py:112-115): voxel rows are grouped by proposal because the
+        # clusters arrive proposal by proposal and sparse_quantize keeps first-occurrence order
+        indices = feats.coordinates[:, 0]
+        batch_offset = torch.cumsum(torch.bincount(indices + 1), dim=0).int()
+        pooled = softgroup_ops.global_avg_pool(feats.features.contiguous(), batch_offset)
+        out["cls_scores"] = self.classification_branch(pooled)
+        out["iou_scores"] = self.iou_score(pooled)
+        return out
+
+    def loss(self, data, out):
+        losses = self.base_loss(data, out)
+        if not (self.clustering and out.get("proposals_idx") is not None):
+            return losses
+        cfg = self.cfg
+        pidx = out["proposals_idx"][:, 1].int().contiguous()
+        poff = out["proposals_offset"]
+        ious_on_cluster = common_ops.get_mask_iou_on_cluster(pidx, poff, data["instance_ids"], data["instance_num_point"])
+        fg_inds = data["instance_semantic_cls"] != -1
+        fg_instance_cls = data["instance_semantic_cls"][fg_inds]
+        fg_ious = ious_on_cluster[:, fg_inds]
+        n_prop = fg_ious.size(0)
+        assigned = fg_ious.new_full((n_prop,), -1, dtype=torch.long)
+        max_iou, argmax_iou = fg_ious.max(1)
+        pos = max_iou >= cfg.sg_pos_iou_thr
+        assigned[pos] = argmax_iou[pos]
+        labels = fg_instance_cls.new_full((n_prop,), self.instance_classes)
+        pos = assigned >= 0
+        labels[pos] = fg_instance_cls[assigned[pos]]
+        labels = labels.long()
+        losses["classification_loss"] = F.cross_entropy(out["cls_scores"], labels)
+        mask_cls_label = labels[out["instance_batch_idxs"].long()]
+        rows = torch.arange(mask_cls_label.size(0), device=labels.device)
+        mask_sig = out["mask_scores"].sigmoid()[rows, mask_cls_label]
+        mask_label, mask_label_mask = common_ops.get_mask_label(
+            pidx, poff, data["instance_ids"], data["instance_semantic_cls"], data["instance_num_point"],
+            ious_on_cluster, -1, cfg.sg_pos_iou_thr)
+        msl = F.binary_cross_entropy(mask_sig, mask_label.float(), weight=mask_label_mask.float(), reduction="sum")
+        losses["mask_scoring_loss"] = msl / (torch.count_nonzero(mask_label_mask) + 1)
+        ious = common_ops.get_mask_iou_on_pred(pidx, poff, data["instance_ids"], data["instance_num_point"],
+                                               mask_sig.detach().contiguous())
+        rows = torch.arange(labels.size(0), device=labels.device)
+        weight = labels < self.instance_classes
+        iou_slice = out["iou_scores"][rows, labels]
+        iou_loss = F.mse_loss(iou_slice, ious[:, fg_inds].max(1)[0], reduction="none")
+        losses["iou_scoring_loss"] = iou_loss[weight].sum() / (weight.count_nonzero() + 1)
+        return losses
+
+
+MODELS = {"pointgroup": PointGroup, "hais": HAIS, "softgroup": SoftGroup}
+
+
+def build_model(cfg: Config):
+    return MODELS[cfg.model](cfg)

@@ -1,0 +1,356 @@
+"""Tensor-level wrappers over the C ABI (include/b2s.h).  torch = memory + streams only.
+
+Every function validates dtype/device/contiguity (TypeError / ValueError, mirroring the
+reference wrappers' asserts, minsu3d/common_ops/functions/common_ops.py:27-29) and then passes raw
+device pointers and the current stream to libb2s.  No function here has a CPU branch.
+"""
+import torch
+
+from . import _cabi
+from ._cabi import check, lib, ptr, require, require_cuda, stream, workspace
+
+I32 = torch.int32
+
+
+def _dev_i32(n, device):
+    return torch.empty(n, dtype=I32, device=device)
+
+
+# ------------------------------------------------------------------------------------------
+# T1 / V1 coordinate hash
+# ------------------------------------------------------------------------------------------
+class HashTable:
+    """Open-addressing coordinate table living in torch-owned device memory."""
+
+    __slots__ = ("keys", "vals", "cap")
+
+    def __init__(self, n, device):
+        self.cap = int(lib().b2s_hash_capacity(int(n)))
+        self.keys = torch.empty(self.cap, dtype=torch.int64, device=device)
+        self.vals = torch.empty(self.cap, dtype=I32, device=device)
+
+
+def coord_unique(coords, quant=1):
+    """First-occurrence unique of int32 [n,4] coordinates (optionally floor-quantised).
+
+    Returns (table, unique_idx[m] i32, inverse[n] i32, out_coords[m,4] i32).  One host read of m.
+    """
+    require_cuda(coords)
+    require(coords.dtype == I32 and coords.dim() == 2 and coords.size(1) == 4 and coords.is_contiguous(),
+            "coords must be a contiguous int32 [n,4] tensor")
+    n = coords.size(0)
+    dev = coords.device
+    table = HashTable(n, dev)
+    unique_idx = _dev_i32(n, dev)
+    inverse = _dev_i32(n, dev)
+    out_coords = torch.empty((n, 4), dtype=I32, device=dev)
+    d_count = _dev_i32(2, dev)
+    nbytes = lib().b2s_coord_unique_ws_bytes(n)
+    ws = workspace(nbytes, dev)
+    check(lib().b2s_coord_unique(ptr(coords), n, int(quant), ptr(table.keys), ptr(table.vals), table.cap,
+                                 ptr(unique_idx), ptr(inverse), ptr(out_coords), ptr(d_count), ptr(ws),
+                                 ws.numel(), stream()), "coord_unique")
+    m, bad = d_count.tolist()
+    if bad:
+        raise ValueError("coordinate outside the packable range (batch < 2^19, |xyz| < 2^14)")
+    return table, unique_idx[:m], inverse, out_coords[:m]
+
+
+def kernel_map(out_coords, table, ksize, dil):
+    """Output-stationary neighbour table nbr[n_out, ksize^3] (int32, -1 = no input)."""
+    require_cuda(out_coords)
+    require(out_coords.dtype == I32 and out_coords.is_contiguous(), "out_coords must be contiguous int32")
+    n_out = out_coords.size(0)
+    K = ksize ** 3
+    nbr = torch.empty((n_out, K), dtype=I32, device=out_coords.device)
+    check(lib().b2s_kernel_map(ptr(out_coords), n_out, int(ksize), int(dil), ptr(table.keys), ptr(table.vals),
+                               table.cap, ptr(nbr), stream()), "kernel_map")
+    return nbr
+
+
+def pairs_from_nbr(nbr, exact=False):
+    """Canonical pair lists: (pair_in, pair_out, k_offsets[K+1], d_count[1]) sorted by (k, out row).
+
+    Arrays are allocated at the n_out*K upper bound (no host sync); pass exact=True to trim.
+    """
+    n_out, K = nbr.shape
+    dev = nbr.device
+    cap = max(n_out * K, 1)
+    pair_in = _dev_i32(cap, dev)
+    pair_out = _dev_i32(cap, dev)
+    k_offsets = _dev_i32(K + 1, dev)
+    d_count = _dev_i32(1, dev)
+    ws = workspace(lib().b2s_pairs_ws_bytes(n_out, K), dev)
+    check(lib().b2s_pairs_from_nbr(ptr(nbr), n_out, K, cap, ptr(pair_in), ptr(pair_out), ptr(k_offsets),
+                                   ptr(d_count), ptr(ws), ws.numel(), stream()), "pairs_from_nbr")
+    if exact:
+        p = int(d_count.item())
+        return pair_in[:p], pair_out[:p], k_offsets, p
+    return pair_in, pair_out, k_offsets, d_count
+
+
+# ------------------------------------------------------------------------------------------
+# T3 / T4 convolution products
+# ------------------------------------------------------------------------------------------
+ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_TF32 = 0, 1, 2, 3
+_default_algo = ALGO_AUTO
+
+
+def set_conv_algo(algo):
+    global _default_algo
+    _default_algo = int(algo)
+
+
+def get_conv_algo():
+    return _default_algo
+
+
+def _f32c(t, name):
+    require_cuda(t)
+    require(t.dtype == torch.float32 and t.is_contiguous(), "%s must be contiguous float32" % name)
+
+
+def conv_table(A, W, nbr, n_out, K, c_in, c_out, w_transposed=False, k_reversed=False, algo=None):
+    _f32c(A, "A")
+    _f32c(W, "W")
+    out = torch.empty((n_out, c_out), dtype=torch.float32, device=A.device)
+    check(lib().b2s_conv_table(ptr(A), ptr(W), ptr(nbr), ptr(out), n_out, K, c_in, c_out, int(w_transposed),
+                               int(k_reversed), _default_algo if algo is None else algo, stream()), "conv_table")
+    return out
+
+
+def conv_pairs(A, W, src, dst, k_offsets, n_out, K, c_in, c_out, max_pairs, w_transposed=False,
+               zero_init=False, algo=None):
+    _f32c(A, "A")
+    _f32c(W, "W")
+    alloc = torch.zeros if zero_init else torch.empty
+    out = alloc((n_out, c_out), dtype=torch.float32, device=A.device)
+    check(lib().b2s_conv_pairs(ptr(A), ptr(W), ptr(src), ptr(dst), ptr(k_offsets), ptr(out), K, c_in, c_out,
+                               int(w_transposed), int(max_pairs), _default_algo if algo is None else algo,
+                               stream()), "conv_pairs")
+    return out
+
+
+def conv_wgrad(A, G, src, dst, k_offsets, K, c_a, c_g, max_pairs, algo=None):
+    _f32c(A, "A")
+    _f32c(G, "G")
+    gW = torch.empty((K, c_a, c_g), dtype=torch.float32, device=A.device)
+    check(lib().b2s_conv_wgrad(ptr(A), ptr(G), ptr(src), ptr(dst), ptr(k_offsets), ptr(gW), K, c_a, c_g,
+                               int(max_pairs), _default_algo if algo is None else algo, stream()), "conv_wgrad")
+    return gW
+
+
+# ------------------------------------------------------------------------------------------
+# T5 batch norm
+# ------------------------------------------------------------------------------------------
+def bn_stats(x):
+    _f32c(x, "x")
+    n, c = x.shape
+    mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    var = torch.empty(c, dtype=torch.float32, device=x.device)
+    ws = workspace(lib().b2s_bn_ws_bytes(n, c), x.device)
+    check(lib().b2s_bn_stats(ptr(x), n, c, 0.0, ptr(mean), ptr(var), ptr(ws), ws.numel(), stream()), "bn_stats")
+    return mean, var
+
+
+def bn_apply(x, mean, rstd, gamma, beta, relu, out=None):
+    _f32c(x, "x")
+    n, c = x.shape
+    y = torch.empty_like(x) if out is None else out
+    check(lib().b2s_bn_apply(ptr(x), n, c, ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), int(relu), ptr(y),
+                             stream()), "bn_apply")
+    return y
+
+
+def bn_backward(x, y, dy, mean, rstd, gamma, relu, training):
+    _f32c(x, "x")
+    _f32c(dy, "dy")
+    n, c = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    ws = workspace(lib().b2s_bn_ws_bytes(n, c), x.device)
+    check(lib().b2s_bn_backward(ptr(x), ptr(y), ptr(dy), n, c, ptr(mean), ptr(rstd), ptr(gamma), int(relu),
+                                int(training), ptr(dx), ptr(dgamma), ptr(dbeta), ptr(ws), ws.numel(), stream()),
+          "bn_backward")
+    return dx, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------
+# V2 devoxelise
+# ------------------------------------------------------------------------------------------
+class _Devoxelize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, idx):
+        _f32c(feat, "feat")
+        require_cuda(idx)
+        require(idx.dtype == torch.int64 and idx.is_contiguous(), "idx must be contiguous int64")
+        n, c = idx.numel(), feat.size(1)
+        out = torch.empty((n, c), dtype=torch.float32, device=feat.device)
+        check(lib().b2s_gather_rows(ptr(feat), ptr(idx), n, c, ptr(out), stream()), "gather_rows")
+        ctx.save_for_backward(idx)
+        ctx.m = feat.size(0)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (idx,) = ctx.saved_tensors
+        grad = grad.contiguous()
+        n, c = grad.shape
+        gfeat = torch.zeros((ctx.m, c), dtype=torch.float32, device=grad.device)
+        check(lib().b2s_scatter_add_rows(ptr(grad), ptr(idx), n, c, ptr(gfeat), stream()), "scatter_add_rows")
+        return gfeat, None
+
+
+def devoxelize(feat, idx):
+    """feat[idx] with a vectorised scatter-add gradient (backbone.py:40, pointgroup.py:88)."""
+    return _Devoxelize.apply(feat, idx)
+
+
+# ------------------------------------------------------------------------------------------
+# C1 ball query
+# ------------------------------------------------------------------------------------------
+def ballquery(coords, batch_idxs, batch_offsets, radius):
+    """Returns (idx[nActive] i32, start_len[n,2] i32); one host read of nActive."""
+    require_cuda(coords, batch_idxs, batch_offsets)
+    require(coords.dtype == torch.float32 and coords.is_contiguous() and coords.dim() == 2 and coords.size(1) == 3,
+            "coords must be contiguous float32 [n,3]")
+    require(batch_idxs.dtype == torch.uint8 and batch_idxs.is_contiguous(), "batch_idxs must be contiguous uint8")
+    require(batch_offsets.dtype == I32 and batch_offsets.is_contiguous(), "batch_offsets must be contiguous int32")
+    n = coords.size(0)
+    dev = coords.device
+    start_len = torch.empty((n, 2), dtype=I32, device=dev)
+    d_count = _dev_i32(1, dev)
+    ws = workspace(lib().b2s_ballquery_ws_bytes(n), dev)
+    nb = batch_offsets.numel() - 1
+    check(lib().b2s_ballquery_count(ptr(coords), ptr(batch_idxs), ptr(batch_offsets), n, nb, float(radius),
+                                    ptr(start_len), ptr(d_count), ptr(ws), ws.numel(), stream()), "ballquery_count")
+    n_active = int(d_count.item()) if n > 0 else 0
+    idx = _dev_i32(n_active, dev)
+    if n_active > 0:
+        check(lib().b2s_ballquery_fill(ptr(coords), ptr(batch_idxs), ptr(batch_offsets), n, nb, float(radius),
+                                       ptr(start_len), ptr(idx), ptr(ws), ws.numel(), stream()), "ballquery_fill")
+    return idx, start_len
+
+
+# ------------------------------------------------------------------------------------------
+# C2 / C3 / C4 clustering
+# ------------------------------------------------------------------------------------------
+def cluster_label(nbr_idx, start_len, labels=None):
+    require_cuda(nbr_idx, start_len, labels)
+    require(nbr_idx.dtype == I32 and start_len.dtype == I32 and nbr_idx.is_contiguous() and start_len.is_contiguous(),
+            "ball query outputs must be contiguous int32")
+    if labels is not None:
+        require(labels.dtype == torch.int16 and labels.is_contiguous(), "labels must be contiguous int16")
+    n = start_len.size(0)
+    comp = _dev_i32(n, start_len.device)
+    ws = workspace(lib().b2s_cluster_ws_bytes(n), start_len.device)
+    check(lib().b2s_cluster_label(ptr(nbr_idx), ptr(start_len), ptr(labels), n, ptr(comp), ptr(ws), ws.numel(),
+                                  stream()), "cluster_label")
+    return comp
+
+
+def cluster_extract(nbr_idx, start_len, labels, comp, mode, thr_i=0, thr_f=0.0, point_num_avg=None, group=0):
+    """select + order: returns (cluster_idxs[S,2] i32, cluster_offsets[nC+1] i32). One host read."""
+    n = start_len.size(0)
+    dev = start_len.device
+    offsets = _dev_i32(n + 1, dev)
+    seeds = _dev_i32(max(n, 1), dev)
+    d_count = _dev_i32(2, dev)
+    ws = workspace(lib().b2s_cluster_ws_bytes(n), dev)
+    check(lib().b2s_cluster_select(ptr(comp), ptr(labels), n, mode, int(thr_i), float(thr_f), ptr(point_num_avg),
+                                   group, ptr(offsets), ptr(seeds), ptr(d_count), ptr(ws), ws.numel(), stream()),
+          "cluster_select")
+    n_cluster, total = d_count.tolist()
+    cluster_idxs = torch.empty((total, 2), dtype=I32, device=dev)
+    offsets = offsets[:n_cluster + 1]
+    if n_cluster > 0:
+        check(lib().b2s_cluster_order(ptr(nbr_idx), ptr(start_len), ptr(labels), ptr(comp), n, ptr(offsets),
+                                      ptr(seeds), n_cluster, ptr(cluster_idxs), ptr(ws), ws.numel(), stream()),
+              "cluster_order")
+    return cluster_idxs, offsets
+
+
+def cluster_centers(cluster_idxs, cluster_offsets, coords, labels, batch_idxs):
+    nc = cluster_offsets.numel() - 1
+    centers = torch.empty((nc, 5), dtype=torch.float32, device=coords.device)
+    check(lib().b2s_cluster_centers(ptr(cluster_idxs), ptr(cluster_offsets), nc, ptr(coords), ptr(labels),
+                                    ptr(batch_idxs), ptr(centers), stream()), "cluster_centers")
+    return centers
+
+
+def ha_set_aggregate(frag_idxs, frag_offsets, frag_centers, prim_idxs, prim_offsets, prim_centers, radius_avg):
+    """HAIS set aggregation; returns (primary_idxs_post[S',2], primary_offsets_post[nP+1])."""
+    dev = prim_idxs.device
+    n_frag = frag_offsets.numel() - 1
+    n_prim = prim_offsets.numel() - 1
+    assign = torch.full((max(n_frag, 1),), -1, dtype=I32, device=dev)
+    check(lib().b2s_ha_assign(ptr(frag_centers), n_frag, ptr(prim_centers), ptr(prim_offsets), n_prim,
+                              ptr(radius_avg), ptr(assign), stream()), "ha_assign")
+    out_idxs = torch.empty((frag_idxs.size(0) + prim_idxs.size(0), 2), dtype=I32, device=dev)
+    out_offsets = torch.zeros(n_prim + 1, dtype=I32, device=dev)
+    ws = workspace(lib().b2s_ha_concat_ws_bytes(n_frag, n_prim), dev)
+    check(lib().b2s_ha_concat(ptr(frag_idxs), ptr(frag_offsets), n_frag, ptr(prim_idxs), ptr(prim_offsets), n_prim,
+                              ptr(assign), ptr(out_idxs), ptr(out_offsets), ptr(ws), ws.numel(), stream()),
+          "ha_concat")
+    return out_idxs, out_offsets, assign[:n_frag]
+
+
+# ------------------------------------------------------------------------------------------
+# S1-S3, I1-I2
+# ------------------------------------------------------------------------------------------
+def _seg(fn_name, inp, offsets, out, *extra):
+    n_seg = offsets.numel() - 1
+    c = inp.size(1)
+    fn = getattr(lib(), fn_name)
+    check(fn(ptr(inp), ptr(offsets), ptr(out), *[ptr(e) for e in extra], n_seg, c, stream()), fn_name)
+
+
+def sec_reduce(kind, inp, offsets, out):
+    _f32c(inp, "inp")
+    require_cuda(offsets, out)
+    require(offsets.dtype == I32 and offsets.is_contiguous(), "offsets must be contiguous int32")
+    _seg({"mean": "b2s_sec_mean", "min": "b2s_sec_min", "max": "b2s_sec_max",
+          "avg": "b2s_global_avg_pool_fp"}[kind], inp, offsets, out)
+    return out
+
+
+def roipool_fp(feats, offsets, out, maxidx):
+    _f32c(feats, "feats")
+    require(offsets.dtype == I32 and offsets.is_contiguous(), "offsets must be contiguous int32")
+    _seg("b2s_roipool_fp", feats, offsets, out, maxidx)
+
+
+def roipool_bp(d_feats, offsets, maxidx, d_out):
+    n_seg, c = d_out.shape
+    check(lib().b2s_roipool_bp(ptr(d_feats), ptr(offsets), ptr(maxidx), ptr(d_out), n_seg, c, stream()), "roipool_bp")
+
+
+def global_avg_pool_bp(d_feats, offsets, d_out):
+    n_seg, c = d_out.shape
+    check(lib().b2s_global_avg_pool_bp(ptr(d_feats), ptr(offsets), ptr(d_out), n_seg, c, stream()),
+          "global_avg_pool_bp")
+
+
+def get_iou(proposals_idx, proposals_offset, instance_labels, instance_pointnum, proposals_iou, mask_scores=None):
+    require_cuda(proposals_idx, proposals_offset, instance_labels, instance_pointnum, proposals_iou, mask_scores)
+    require(proposals_idx.dtype == I32 and proposals_offset.dtype == I32 and instance_pointnum.dtype == I32,
+            "proposals_idx / proposals_offset / instance_pointnum must be int32")
+    require(instance_labels.dtype == torch.int16, "instance labels must be int16")
+    n_inst = instance_pointnum.numel()
+    n_prop = proposals_offset.numel() - 1
+    check(lib().b2s_get_iou(ptr(proposals_idx), ptr(proposals_offset), ptr(instance_labels), ptr(instance_pointnum),
+                            ptr(mask_scores), ptr(proposals_iou), n_inst, n_prop, stream()), "get_iou")
+    return proposals_iou
+
+
+def get_mask_label(proposals_idx, proposals_offset, instance_labels, instance_cls, proposals_iou, n_inst, n_prop,
+                   ignored_label, iou_thr, mask_label, mask_label_mask):
+    require_cuda(proposals_idx, proposals_offset, instance_labels, instance_cls, proposals_iou)
+    require(instance_cls.dtype == torch.int16 and instance_labels.dtype == torch.int16, "labels must be int16")
+    check(lib().b2s_get_mask_label(ptr(proposals_idx), ptr(proposals_offset), ptr(instance_labels),
+                                   ptr(instance_cls), ptr(proposals_iou), n_inst, n_prop, int(ignored_label),
+                                   float(iou_thr), ptr(mask_label), ptr(mask_label_mask), stream()), "get_mask_label")
+
+
+__all__ = [n for n in dir() if not n.startswith("_")]

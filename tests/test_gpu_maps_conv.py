@@ -1,0 +1,255 @@
+"""GPU parity: coordinate hash / kernel maps (bit-exact) and sparse convolution (fp32 tolerance).
+
+CUDA path (libb2s through the C ABI) vs the CPU oracle (oracle/oracle.c) on identical seeded inputs.
+Tolerance for fp32 features/gradients: 1e-4 relative to the output's max-abs (BASELINE.json
+north_star's example tolerance); integer/index results must be bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import random_voxels, surface_voxels
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _close(got, want, tol=RTOL):
+    got, want = got.detach().cpu().double().numpy(), np.asarray(want, np.float64)
+    assert got.shape == want.shape
+    scale = max(np.abs(want).max(), 1e-6)
+    err = np.abs(got - want).max() / scale
+    assert err < tol, "max rel err %.3e" % err
+
+
+@pytest.mark.parametrize("n,dup", [(0, 0.0), (1, 0.0), (5000, 0.3), (200_000, 0.2)])
+def test_coord_unique_matches_oracle(n, dup):
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(n + 1)
+    c = random_voxels(rng, n, dup=dup) if n else np.zeros((0, 4), np.int32)
+    ui, inv, oc = oracle.coord_unique(c, 1)
+    table, g_ui, g_inv, g_oc = ops.coord_unique(_dev(c), 1)
+    assert np.array_equal(g_ui.cpu().numpy(), ui)
+    assert np.array_equal(g_inv.cpu().numpy(), inv)
+    assert np.array_equal(g_oc.cpu().numpy(), oc)
+
+
+@pytest.mark.parametrize("quant", [2, 4, 16])
+def test_stride_map_matches_oracle(quant):
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(quant)
+    c = random_voxels(rng, 50_000)
+    c[:, 1:] = (c[:, 1:] // (quant // 2)) * (quant // 2)  # input lives on stride quant/2
+    c = oracle.coord_unique(c, 1)[2]
+    ui, inv, oc = oracle.coord_unique(c, quant)
+    _, g_ui, g_inv, g_oc = ops.coord_unique(_dev(c), quant)
+    assert np.array_equal(g_oc.cpu().numpy(), oc)
+    assert np.array_equal(g_inv.cpu().numpy(), inv)
+
+
+def test_coord_range_error():
+    from minsu3d_b200 import ops
+    c = np.array([[0, 0, 0, 0], [0, 20000, 0, 0]], np.int32)
+    with pytest.raises(ValueError):
+        ops.coord_unique(_dev(c), 1)
+
+
+@pytest.mark.parametrize("ksize,n", [(3, 3000), (3, 120_000), (1, 1000), (5, 2000)])
+def test_kernel_map_and_pairs_bit_exact(ksize, n):
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(ksize * 7 + n)
+    c = surface_voxels(rng, n)
+    nbr = oracle.kernel_map(c, c, ksize, 1)
+    table, _, _, oc = ops.coord_unique(_dev(c), 1)
+    g_nbr = ops.kernel_map(oc, table, ksize, 1)
+    assert np.array_equal(g_nbr.cpu().numpy(), nbr)
+    pin, pout, koff = oracle.pairs_from_nbr(nbr)
+    g_in, g_out, g_koff, p = ops.pairs_from_nbr(g_nbr, exact=True)
+    assert p == pin.size
+    assert np.array_equal(g_koff.cpu().numpy(), koff)
+    assert np.array_equal(g_in.cpu().numpy(), pin)
+    assert np.array_equal(g_out.cpu().numpy(), pout)
+    if ksize % 2 == 1:  # symmetry used by the data-gradient kernel: nbr[i, K-1-k] = o <=> nbr[o, k] = i
+        K = ksize ** 3
+        o, k = np.nonzero(nbr >= 0)
+        assert np.array_equal(nbr[nbr[o, k], K - 1 - k], o)
+
+
+def test_strided_kernel_map_bit_exact():
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(3)
+    c = surface_voxels(rng, 60_000)
+    _, inv, oc = oracle.coord_unique(c, 2)
+    nbr = oracle.kernel_map(c, oc, 2, 1)
+    assert (nbr >= 0).sum() == c.shape[0]  # every fine row has exactly one (coarse row, offset)
+    t_in, _, _, c_in = ops.coord_unique(_dev(c), 1)
+    _, _, g_inv, g_oc = ops.coord_unique(c_in, 2)
+    g_nbr = ops.kernel_map(g_oc, t_in, 2, 1)
+    assert np.array_equal(g_oc.cpu().numpy(), oc)
+    assert np.array_equal(g_nbr.cpu().numpy(), nbr)
+    # the parent found through the table equals the inverse map of the stride insert
+    o, k = np.nonzero(nbr >= 0)
+    assert np.array_equal(inv[nbr[o, k]], o)
+
+
+CONV_SHAPES = [(6, 16), (16, 16), (32, 16), (32, 32), (48, 48), (64, 32), (64, 64), (96, 112), (224, 224), (20, 24)]
+
+
+@pytest.mark.parametrize("cin,cout", CONV_SHAPES)
+def test_conv3_forward_backward(cin, cout):
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(cin * 1000 + cout)
+    n = 6000 if cin * cout > 4096 else 20_000
+    c = surface_voxels(rng, n)
+    n = c.shape[0]
+    nbr = oracle.kernel_map(c, c, 3, 1)
+    x = rng.standard_normal((n, cin)).astype(np.float32)
+    w = (rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32)
+    g = rng.standard_normal((n, cout)).astype(np.float32)
+    want = oracle.conv_fwd(x, w, nbr, n)
+    want_gin, want_gw = oracle.conv_bwd(x, w, g, nbr)
+    d_nbr = _dev(nbr)
+    got = ops.conv_table(_dev(x), _dev(w), d_nbr, n, 27, cin, cout, algo=ops.ALGO_SIMT)
+    _close(got, want)
+    gin = ops.conv_table(_dev(g), _dev(w), d_nbr, n, 27, cout, cin, w_transposed=True, k_reversed=True,
+                         algo=ops.ALGO_SIMT)
+    _close(gin, want_gin)
+    pin, pout, koff, maxp = ops.pairs_from_nbr(d_nbr)[:3] + (n * 27,)
+    gw = ops.conv_wgrad(_dev(x), _dev(g), pin, pout, koff, 27, cin, cout, maxp, algo=ops.ALGO_SIMT)
+    _close(gw, want_gw)
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 32), (32, 48), (112, 96), (64, 32)])
+def test_strided_and_transposed_conv_modules(cin, cout):
+    """MinkowskiConvolution(k=2,s=2) and MinkowskiConvolutionTranspose(k=2,s=2) incl. autograd."""
+    from minsu3d_b200 import MinkowskiEngine as ME
+    rng = np.random.default_rng(cin + cout)
+    c = surface_voxels(rng, 15_000)
+    n = c.shape[0]
+    x = rng.standard_normal((n, cin)).astype(np.float32)
+    _, _, oc = oracle.coord_unique(c, 2)
+    m = oc.shape[0]
+    nbr_down = oracle.kernel_map(c, oc, 2, 1)
+    down = ME.MinkowskiConvolution(cin, cout, kernel_size=2, stride=2, dimension=3).cuda()
+    up = ME.MinkowskiConvolutionTranspose(cout, cin, kernel_size=2, stride=2, dimension=3).cuda()
+    xt = _dev(x).requires_grad_(True)
+    st = ME.SparseTensor(features=xt, coordinates=_dev(c))
+    y = down(st)
+    z = up(y)
+    assert np.array_equal(y.C.cpu().numpy(), oc)
+    assert z.coordinate_map_key == st.coordinate_map_key
+    wd = down.kernel.detach().cpu().numpy()
+    wu = up.kernel.detach().cpu().numpy()
+    want_y = oracle.conv_fwd(x, wd, nbr_down, m)
+    want_z = oracle.convT_fwd(want_y, wu, nbr_down, n)
+    _close(y.F, want_y)
+    _close(z.F, want_z)
+    gz = rng.standard_normal((n, cin)).astype(np.float32)
+    z.F.backward(_dev(gz))
+    # oracle gradients by the definition: convT is the adjoint structure of the strided conv
+    gy = np.zeros((m, cout), np.float64)
+    gwu = np.zeros(wu.shape, np.float64)
+    gwd = np.zeros(wd.shape, np.float64)
+    gx = np.zeros((n, cin), np.float64)
+    for k in range(8):
+        o = np.nonzero(nbr_down[:, k] >= 0)[0]
+        i = nbr_down[o, k]
+        gy[o] += gz[i].astype(np.float64) @ wu[k].astype(np.float64).T
+        gwu[k] = want_y[o].astype(np.float64).T @ gz[i].astype(np.float64)
+    for k in range(8):
+        o = np.nonzero(nbr_down[:, k] >= 0)[0]
+        i = nbr_down[o, k]
+        gx[i] = gy[o] @ wd[k].astype(np.float64).T
+        gwd[k] = x[i].astype(np.float64).T @ gy[o]
+    _close(up.kernel.grad, gwu)
+    _close(down.kernel.grad, gwd)
+    _close(xt.grad, gx)
+
+
+def test_conv1x1_and_empty():
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((5000, 32)).astype(np.float32)
+    w = rng.standard_normal((32, 16)).astype(np.float32)
+    got = ops.conv_table(_dev(x), _dev(w), None, 5000, 1, 32, 16, algo=ops.ALGO_SIMT)
+    _close(got, x.astype(np.float64) @ w.astype(np.float64))
+    empty = ops.conv_table(_dev(x[:0]), _dev(w), None, 0, 1, 32, 16, algo=ops.ALGO_SIMT)
+    assert empty.shape == (0, 16)
+
+
+def test_sparse_conv_equals_dense_conv3d():
+    """Independent of the oracle: scatter to a dense grid and run torch conv3d (appendix A cross-check)."""
+    from minsu3d_b200 import MinkowskiEngine as ME
+    rng = np.random.default_rng(11)
+    c = random_voxels(rng, 4000, extent=16, batch=2)
+    c[:, 1:] = np.abs(c[:, 1:]) % 12
+    c = oracle.coord_unique(c, 1)[2]
+    n, cin, cout = c.shape[0], 8, 12
+    x = rng.standard_normal((n, cin)).astype(np.float32)
+    conv = ME.MinkowskiConvolution(cin, cout, kernel_size=3, dimension=3).cuda()
+    y = conv(ME.SparseTensor(features=_dev(x), coordinates=_dev(c))).F.detach().cpu()
+    dense = torch.zeros(2, cin, 12, 12, 12, dtype=torch.float64)
+    ct = torch.from_numpy(c).long()
+    dense[ct[:, 0], :, ct[:, 3], ct[:, 2], ct[:, 1]] = torch.from_numpy(x).double()
+    k = conv.kernel.detach().cpu().double()  # [27, cin, cout], kidx = ix + 3 iy + 9 iz
+    wd = k.view(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2)  # [cout, cin, iz, iy, ix]
+    out = torch.nn.functional.conv3d(dense, wd, padding=1)
+    want = out[ct[:, 0], :, ct[:, 3], ct[:, 2], ct[:, 1]]
+    _close(y, want.numpy())
+
+
+@pytest.mark.parametrize("c,relu", [(16, True), (32, False), (112, True), (224, True)])
+def test_batchnorm_relu_matches_torch(c, relu):
+    from minsu3d_b200 import MinkowskiEngine as ME
+    rng = np.random.default_rng(c)
+    n = 30_000
+    x = (rng.standard_normal((n, c)) * 2 + 0.5).astype(np.float32)
+    coords = oracle.coord_unique(random_voxels(rng, n, extent=80), 1)[2]
+    n = coords.shape[0]
+    x = x[:n]
+    mod = ME.MinkowskiBatchNorm(c).cuda()
+    ref = torch.nn.BatchNorm1d(c).cuda()
+    with torch.no_grad():
+        mod.bn.weight.uniform_(0.5, 1.5)
+        mod.bn.bias.uniform_(-0.5, 0.5)
+        ref.load_state_dict(mod.bn.state_dict())
+    xa = _dev(x).requires_grad_(True)
+    xb = _dev(x).requires_grad_(True)
+    st = mod(ME.SparseTensor(features=xa, coordinates=_dev(coords)))
+    ya = (ME.MinkowskiReLU(inplace=True)(st) if relu else st).F
+    yb = ref(xb)
+    if relu:
+        # share the ReLU mask: pre-activations within 1e-6 of zero may legitimately land on either side
+        _close(ya, torch.relu(yb).detach().cpu().numpy(), 1e-5)
+        yb = yb * (ya.detach() > 0).float()
+    _close(ya, yb.detach().cpu().numpy(), 1e-5)
+    g = _dev(rng.standard_normal((n, c)).astype(np.float32))
+    ya.backward(g)
+    yb.backward(g)
+    _close(xa.grad, xb.grad.cpu().numpy(), 1e-4)
+    _close(mod.bn.weight.grad, ref.weight.grad.cpu().numpy(), 1e-4)
+    _close(mod.bn.bias.grad, ref.bias.grad.cpu().numpy(), 1e-4)
+    _close(mod.bn.running_mean, ref.running_mean.cpu().numpy(), 1e-5)
+    _close(mod.bn.running_var, ref.running_var.cpu().numpy(), 1e-5)
+
+
+def test_devoxelize_gather_scatter():
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(9)
+    m, n, c = 7000, 20_000, 16
+    feat = rng.standard_normal((m, c)).astype(np.float32)
+    idx = rng.integers(0, m, n)
+    f = _dev(feat).requires_grad_(True)
+    out = ops.devoxelize(f, _dev(idx))
+    assert np.array_equal(out.detach().cpu().numpy(), feat[idx])
+    g = rng.standard_normal((n, c)).astype(np.float32)
+    out.backward(_dev(g))
+    want = np.zeros((m, c), np.float64)
+    np.add.at(want, idx, g.astype(np.float64))
+    _close(f.grad, want, 1e-5)
