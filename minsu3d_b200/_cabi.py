@@ -73,12 +73,48 @@ def lib():
                 "libb2s.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `python minsu3d_b200/csrc/build.py`. There is no CPU fallback." % LIB_PATH)
         handle = ctypes.CDLL(LIB_PATH)
+        ns = _Namespace()
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = handle
+            k = KERNELS_PER_CALL.get(name, 0)
+            setattr(ns, name, _counted(fn, k) if k else fn)
+        _lib = ns
     return _lib
+
+
+class _Namespace:
+    pass
+
+
+# kernels launched by one call of each entry point (CUB scan = 2, 64-bit radix sort ~ 10);
+# used for the `gpu_launches` figure of bench.py
+KERNELS_PER_CALL = {
+    "b2s_coord_unique": 6, "b2s_kernel_map": 1, "b2s_pairs_from_nbr": 4, "b2s_conv_table": 1, "b2s_conv_pairs": 1,
+    "b2s_conv_wgrad": 1, "b2s_bn_stats": 2, "b2s_bn_apply": 1, "b2s_bn_backward": 3, "b2s_gather_rows": 1,
+    "b2s_scatter_add_rows": 1, "b2s_ballquery_count": 16, "b2s_ballquery_fill": 1, "b2s_cluster_label": 1,
+    "b2s_cluster_select": 7, "b2s_cluster_order": 1, "b2s_cluster_centers": 1, "b2s_ha_assign": 1,
+    "b2s_ha_concat": 4, "b2s_sec_mean": 1, "b2s_sec_min": 1, "b2s_sec_max": 1, "b2s_roipool_fp": 1,
+    "b2s_roipool_bp": 1, "b2s_global_avg_pool_fp": 1, "b2s_global_avg_pool_bp": 1, "b2s_get_iou": 1,
+    "b2s_get_mask_label": 1,
+}
+_launches = [0]
+
+
+def _counted(fn, k):
+    def call(*a):
+        _launches[0] += k
+        return fn(*a)
+    return call
+
+
+def reset_launch_count():
+    _launches[0] = 0
+
+
+def launch_count():
+    return _launches[0]
 
 
 def check(rc, what=""):

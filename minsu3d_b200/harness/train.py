@@ -1,0 +1,53 @@
+"""One training step of PointGroup / HAIS / SoftGroup on the B200-native hot path.
+
+Replaces the Lightning loop around `training_step` (minsu3d/model/general_model.py:52-66,
+train.py:35-41) with a plain loop: forward (backbone + clustering + ScoreNet), losses, backward,
+scene-sharded gradient all-reduce (minsu3d_b200.dp) and Adam (config/model/pointgroup.yaml:16-18).
+"""
+import torch
+
+from .. import dp
+from . import models
+
+HOST_KEYS = ("point_xyz", "vert_batch_ids", "sem_labels", "instance_ids", "instance_center_xyz",
+             "instance_num_point", "instance_offsets", "instance_semantic_cls", "voxel_xyz", "voxel_features",
+             "voxel_point_map")
+
+
+def to_pinned_host(data):
+    """Collated batch -> pinned host tensors (what a DataLoader with pin_memory=True hands over)."""
+    out = {}
+    for k, v in data.items():
+        out[k] = v.detach().cpu().pin_memory() if torch.is_tensor(v) else v
+    return out
+
+
+def host_bytes(data):
+    return sum(v.numel() * v.element_size() for v in data.values() if torch.is_tensor(v))
+
+
+class Trainer:
+    def __init__(self, cfg: models.Config, device, bucket_mb=8.0, seed=123):
+        torch.manual_seed(seed)  # config/config.yaml:17
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.model = models.build_model(cfg).to(self.device)
+        self.model.train()
+        self.bucketer = dp.GradBucketer(self.model.parameters(), bucket_mb=bucket_mb)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr)
+        self.last_losses = None
+
+    def step(self, data):
+        """data already on the device.  Returns the total loss (device scalar)."""
+        self.bucketer.zero_grad()
+        total, losses, _ = self.model.training_loss(data)
+        total.backward()
+        self.bucketer.finish()
+        self.optimizer.step()
+        self.last_losses = losses
+        return total.detach()
+
+    def step_from_host(self, host_data):
+        """The user-facing call: pinned host batch in, python float loss out (H2D + D2H inside)."""
+        data = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_data.items()}
+        return float(self.step(data).item())
