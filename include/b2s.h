@@ -96,14 +96,18 @@ int b2s_pairs_from_nbr(const int32_t* nbr, int64_t n_out, int32_t K, int64_t pai
  *     out[dst[p], :] = A[src[p], :] @ Wk   (each dst row appears once; plain store)
  *     transposed-conv forward and strided-conv data gradient.
  * b2s_conv_wgrad: gW[k] (+)= sum_p A[src[p], :]^T @ G[dst[p], :]   (gW zeroed by the callee)
- * algo: 0 = auto, 1 = fp32 FMA (SIMT), 2 = tcgen05 TF32x3 (fp32-class accuracy), 3 = tcgen05 TF32.
+ * algo: 0 = auto (tcgen05 3xTF32 when c_in, c_out are multiples of 16 and c_out <= 256, else fp32 FMA),
+ *       1 = fp32 FMA (SIMT), 2 = tcgen05 3xTF32 (fp32-class accuracy), 3 = tcgen05 plain TF32.
  * ---------------------------------------------------------------------------------------------- */
+size_t b2s_conv_ws_bytes(int32_t K, int32_t c_in, int32_t c_out); /* scratch for the packed weights */
 int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, float* out,
                    int64_t n_out, int32_t K, int32_t c_in, int32_t c_out,
-                   int32_t w_transposed, int32_t k_reversed, int32_t algo, b2s_stream_t stream);
+                   int32_t w_transposed, int32_t k_reversed, int32_t algo,
+                   void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_conv_pairs(const float* A, const float* W, const int32_t* src, const int32_t* dst,
                    const int32_t* k_offsets, float* out, int32_t K, int32_t c_in, int32_t c_out,
-                   int32_t w_transposed, int64_t max_pairs, int32_t algo, b2s_stream_t stream);
+                   int32_t w_transposed, int64_t max_pairs, int32_t algo,
+                   void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_conv_wgrad(const float* A, const float* G, const int32_t* src, const int32_t* dst,
                    const int32_t* k_offsets, float* gW, int32_t K, int32_t c_a, int32_t c_g,
                    int64_t max_pairs, int32_t algo, b2s_stream_t stream);
@@ -111,11 +115,14 @@ int b2s_conv_wgrad(const float* A, const float* G, const int32_t* src, const int
 /* ------------------------------------------------------------------------------------------------
  * T5 -- fused BatchNorm(+ReLU) on sparse-tensor features (MinkowskiBatchNorm + MinkowskiReLU,
  * common.py:13-14,35-39).  Training statistics are biased batch statistics like
- * torch.nn.BatchNorm1d.  stats = [2,C] float (mean, rstd) output of bn_stats.
+ * torch.nn.BatchNorm1d.
  * ---------------------------------------------------------------------------------------------- */
 size_t b2s_bn_ws_bytes(int64_t n, int32_t c);
-int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float* mean, float* var_biased,
-                 void* ws, size_t ws_bytes, b2s_stream_t stream);
+/* batch statistics: mean, biased variance (optional), rstd = 1/sqrt(var+eps) (optional); when
+ * running_mean/var are given they are updated in place with `momentum` and the unbiased variance. */
+int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum, float* running_mean,
+                 float* running_var, float* mean, float* var_biased, float* rstd, void* ws,
+                 size_t ws_bytes, b2s_stream_t stream);
 int b2s_bn_apply(const float* x, int64_t n, int32_t c, const float* mean, const float* rstd,
                  const float* gamma, const float* beta, int32_t relu, float* y, b2s_stream_t stream);
 /* backward of y = relu?(gamma*(x-mean)*rstd + beta) in training mode:

@@ -231,17 +231,11 @@ class _BNReLU(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, relu):
         x = x.contiguous()
-        n = x.size(0)
         if training:
-            mean, var = ops.bn_stats(x)
-            if running_mean is not None:
-                with torch.no_grad():
-                    unbiased = var * (float(n) / max(n - 1, 1))
-                    running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-                    running_var.mul_(1 - momentum).add_(unbiased, alpha=momentum)
+            mean, rstd = ops.bn_stats(x, eps, momentum if running_mean is not None else 0.0, running_mean,
+                                      running_var)
         else:
-            mean, var = running_mean, running_var
-        rstd = torch.rsqrt(var + eps)
+            mean, rstd = running_mean, torch.rsqrt(running_var + eps)
         y = ops.bn_apply(x, mean, rstd, weight, bias, relu)
         ctx.save_for_backward(x, y if relu else x, mean, rstd, weight)
         ctx.relu = relu

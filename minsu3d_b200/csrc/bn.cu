@@ -11,52 +11,79 @@
 namespace b2s {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_SLAB = 1024;  // rows per CTA
+constexpr int BN_SLAB = 512;  // rows per CTA
 
 // partial[blk][2][c] (double): column sums of (p, q) where
 //   mode 0: p = x,            q = x*x
 //   mode 1: p = dy*mask(y),   q = dy*mask(y) * (x-mean)*rstd
+// Thread t owns the float4 column (t % c4) and the row phase (t / c4); four independent 16-byte
+// loads are in flight per thread and array, fp32 partials are flushed into double every 32 rows.
 __global__ void __launch_bounds__(BN_THREADS)
     bn_colsum_kernel(const float* __restrict__ x, const float* __restrict__ y,
                      const float* __restrict__ dy, const float* __restrict__ mean,
                      const float* __restrict__ rstd, int64_t n, int c, int mode, int relu,
                      double* __restrict__ partial) {
   extern __shared__ double s_acc[];  // [rpp][2][c]
-  const int rpp = BN_THREADS / c > 0 ? BN_THREADS / c : 1;  // row phases per pass
-  const int ch0 = threadIdx.x % c, ph = threadIdx.x / c;
+  const int c4 = c >> 2;
+  const int rpp = BN_THREADS / c4 > 0 ? BN_THREADS / c4 : 1;  // row phases per pass
   const int64_t r0 = (int64_t)blockIdx.x * BN_SLAB;
   const int64_t r1 = min(n, r0 + BN_SLAB);
-  // channels handled by this thread: ch0, ch0 + BN_THREADS (only when c > BN_THREADS)
-  for (int ch = ch0; ch < c; ch += BN_THREADS) {
-    double dp = 0.0, dq = 0.0;
-    if (ph < rpp) {
-      float m = 0.f, rs = 1.f;
-      if (mode == 1) {
-        m = mean[ch];
-        rs = rstd[ch];
+  for (int vc = threadIdx.x % c4, ph = threadIdx.x / c4; vc < c4 && ph < rpp; vc += BN_THREADS) {
+    double dp[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+    float p[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    float4 m4 = make_float4(0, 0, 0, 0), rs4 = make_float4(1, 1, 1, 1);
+    if (mode == 1) {
+      m4 = __ldg((const float4*)mean + vc);
+      rs4 = __ldg((const float4*)rstd + vc);
+    }
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+    int cnt = 0;
+    for (int64_t r = r0 + ph; r < r1; r += 4 * (int64_t)rpp) {
+      float4 xv[4], gv[4], yv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int64_t rr = r + (int64_t)u * rpp;
+        bool ok = rr < r1;
+        int64_t i = rr * c4 + vc;
+        xv[u] = ok ? __ldg((const float4*)x + i) : make_float4(0, 0, 0, 0);
+        if (mode == 1) {
+          gv[u] = ok ? __ldg((const float4*)dy + i) : make_float4(0, 0, 0, 0);
+          yv[u] = (ok && relu) ? __ldg((const float4*)y + i) : make_float4(1, 1, 1, 1);
+          if (!ok) xv[u] = m4;  // (x - mean) = 0 for padding rows
+        }
       }
-      float p = 0.f, q = 0.f;
-      int cnt = 0;
-      for (int64_t r = r0 + ph; r < r1; r += rpp) {
-        int64_t i = r * c + ch;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
         if (mode == 0) {
-          float v = __ldg(x + i);
-          p += v;
-          q = fmaf(v, v, q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            p[j] += xs[j];
+            q[j] = fmaf(xs[j], xs[j], q[j]);
+          }
         } else {
-          float g = __ldg(dy + i);
-          if (relu && !(__ldg(y + i) > 0.f)) g = 0.f;
-          p += g;
-          q = fmaf(g, (__ldg(x + i) - m) * rs, q);
-        }
-        if (++cnt == 64) {  // flush fp32 run into double
-          dp += p; dq += q; p = 0.f; q = 0.f; cnt = 0;
+          float gs[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+          float ys[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float g = (relu && !(ys[j] > 0.f)) ? 0.f : gs[j];
+            p[j] += g;
+            q[j] = fmaf(g, (xs[j] - m[j]) * rs[j], q[j]);
+          }
         }
       }
-      dp += p;
-      dq += q;
-      s_acc[(ph * 2 + 0) * c + ch] = dp;
-      s_acc[(ph * 2 + 1) * c + ch] = dq;
+      if (++cnt == 8) {  // 32 rows accumulated in fp32
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dp[j] += p[j]; dq[j] += q[j]; p[j] = 0.f; q[j] = 0.f;
+        }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s_acc[(ph * 2 + 0) * c + vc * 4 + j] = dp[j] + p[j];
+      s_acc[(ph * 2 + 1) * c + vc * 4 + j] = dq[j] + q[j];
     }
   }
   __syncthreads();
@@ -71,32 +98,59 @@ __global__ void __launch_bounds__(BN_THREADS)
   }
 }
 
-__global__ void __launch_bounds__(BN_THREADS)
-    bn_finish_stats_kernel(const double* __restrict__ partial, int nblk, int64_t n, int c,
-                           float* __restrict__ mean, float* __restrict__ var) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  double sp = 0.0, sq = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    sp += partial[((int64_t)b * 2 + 0) * c + ch];
-    sq += partial[((int64_t)b * 2 + 1) * c + ch];
+// deterministic second stage: 32 channels x 8 block-groups per CTA, fixed summation order
+__device__ __forceinline__ void bn_reduce_partials(const double* __restrict__ partial, int nblk, int c,
+                                                   double& sp, double& sq, int& ch) {
+  __shared__ double s_p[8][33], s_q[8][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  ch = blockIdx.x * 32 + lane;
+  double a = 0.0, b = 0.0;
+  if (ch < c)
+    for (int blk = grp; blk < nblk; blk += 8) {
+      a += partial[((int64_t)blk * 2 + 0) * c + ch];
+      b += partial[((int64_t)blk * 2 + 1) * c + ch];
+    }
+  s_p[grp][lane] = a;
+  s_q[grp][lane] = b;
+  __syncthreads();
+  sp = 0.0;
+  sq = 0.0;
+  for (int g = 0; g < 8; ++g) {
+    sp += s_p[g][lane];
+    sq += s_q[g][lane];
   }
+}
+
+// mean / rstd (+ running statistics with momentum, unbiased variance like torch.nn.BatchNorm1d)
+__global__ void __launch_bounds__(BN_THREADS)
+    bn_finish_stats_kernel(const double* __restrict__ partial, int nblk, int64_t n, int c, float eps,
+                           float momentum, float* __restrict__ running_mean,
+                           float* __restrict__ running_var, float* __restrict__ mean,
+                           float* __restrict__ var, float* __restrict__ rstd) {
+  double sp, sq;
+  int ch;
+  bn_reduce_partials(partial, nblk, c, sp, sq, ch);
+  if (threadIdx.x >= 32 || ch >= c) return;
   double m = sp / (double)n;
   double v = sq / (double)n - m * m;
+  v = v > 0.0 ? v : 0.0;
   mean[ch] = (float)m;
-  var[ch] = (float)(v > 0.0 ? v : 0.0);
+  if (var) var[ch] = (float)v;
+  if (rstd) rstd[ch] = (float)(1.0 / sqrt(v + (double)eps));
+  if (running_mean) {
+    double unbiased = n > 1 ? v * ((double)n / (double)(n - 1)) : v;
+    running_mean[ch] = (float)((1.0 - (double)momentum) * (double)running_mean[ch] + (double)momentum * m);
+    running_var[ch] = (float)((1.0 - (double)momentum) * (double)running_var[ch] + (double)momentum * unbiased);
+  }
 }
 
 __global__ void __launch_bounds__(BN_THREADS)
     bn_finish_grad_kernel(const double* __restrict__ partial, int nblk, int c,
                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  double sp = 0.0, sq = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    sp += partial[((int64_t)b * 2 + 0) * c + ch];
-    sq += partial[((int64_t)b * 2 + 1) * c + ch];
-  }
+  double sp, sq;
+  int ch;
+  bn_reduce_partials(partial, nblk, c, sp, sq, ch);
+  if (threadIdx.x >= 32 || ch >= c) return;
   dbeta[ch] = (float)sp;
   dgamma[ch] = (float)sq;
 }
@@ -171,13 +225,14 @@ static int bn_check(int64_t n, int32_t c) {
 }
 
 static size_t bn_smem(int c) {
-  int rpp = BN_THREADS / c > 0 ? BN_THREADS / c : 1;
+  int c4 = c / 4;
+  int rpp = BN_THREADS / c4 > 0 ? BN_THREADS / c4 : 1;
   return (size_t)rpp * 2 * c * 8;
 }
 
-int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float* mean, float* var_biased,
-                 void* ws, size_t ws_bytes, b2s_stream_t stream) {
-  (void)eps;
+int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum, float* running_mean,
+                 float* running_var, float* mean, float* var_biased, float* rstd, void* ws, size_t ws_bytes,
+                 b2s_stream_t stream) {
   int rc = bn_check(n, c);
   if (rc) return rc;
   if (n == 0) return B2S_OK;
@@ -188,7 +243,8 @@ int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float* mean, f
   }
   double* partial = (double*)ws;
   bn_colsum_kernel<<<nblk, BN_THREADS, bn_smem(c), stream>>>(x, nullptr, nullptr, nullptr, nullptr, n, c, 0, 0, partial);
-  bn_finish_stats_kernel<<<(unsigned)cdiv(c, BN_THREADS), BN_THREADS, 0, stream>>>(partial, nblk, n, c, mean, var_biased);
+  bn_finish_stats_kernel<<<(unsigned)cdiv(c, 32), BN_THREADS, 0, stream>>>(partial, nblk, n, c, eps, momentum, running_mean,
+                                                                           running_var, mean, var_biased, rstd);
   return check_launch("bn_stats");
 }
 
@@ -221,7 +277,7 @@ int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, 
   }
   double* partial = (double*)ws;
   bn_colsum_kernel<<<nblk, BN_THREADS, bn_smem(c), stream>>>(x, y, dy, mean, rstd, n, c, 1, relu, partial);
-  bn_finish_grad_kernel<<<(unsigned)cdiv(c, BN_THREADS), BN_THREADS, 0, stream>>>(partial, nblk, c, dgamma, dbeta);
+  bn_finish_grad_kernel<<<(unsigned)cdiv(c, 32), BN_THREADS, 0, stream>>>(partial, nblk, c, dgamma, dbeta);
   int64_t total4 = n * (c / 4);
   bn_dx_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, stream>>>(
       (const float4*)x, (const float4*)y, (const float4*)dy, total4, c / 4, 1.0f / (float)n, mean, rstd,

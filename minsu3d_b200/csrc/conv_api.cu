@@ -5,40 +5,66 @@ namespace b2s {
 int conv_table_simt(const float*, const float*, const int32_t*, float*, int64_t, int, int, int, int, int, cudaStream_t);
 int conv_pairs_simt(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, float*, int, int, int, int, int64_t, cudaStream_t);
 int conv_wgrad_simt(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, float*, int, int, int, int64_t, cudaStream_t);
-// tcgen05 path (conv_tc.cu); returns B2S_E_INVALID when the shape is unsupported
-int conv_table_tc(const float*, const float*, const int32_t*, float*, int64_t, int, int, int, int, int, int, cudaStream_t);
+// tcgen05 path (conv_tc.cu)
 bool conv_tc_supported(int K, int c_in, int c_out);
+size_t conv_tc_ws_bytes(int K, int c_in, int c_out);
+int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* dst, const int32_t* k_offsets,
+            float* out, int64_t n_out, int64_t max_pairs, int K, int c_in, int c_out, int wT, int krev, int nsplit,
+            bool pairs, void* ws, size_t ws_bytes, cudaStream_t stream);
 }  // namespace b2s
 
 using namespace b2s;
 
+// algo: 0 auto (tcgen05 3xTF32 when the shape allows, else fp32 FMA), 1 fp32 FMA, 2 tcgen05 3xTF32, 3 tcgen05 TF32
+static int pick(int algo, int K, int c_in, int c_out, const char* what, int* nsplit) {
+  bool ok = conv_tc_supported(K, c_in, c_out);
+  if (algo == 0) algo = ok ? 2 : 1;
+  if ((algo == 2 || algo == 3) && !ok) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "%s: shape (K=%d, c_in=%d, c_out=%d) not supported by the tcgen05 path", what, K, c_in, c_out);
+    set_error(buf);
+    return -1;
+  }
+  *nsplit = algo == 2 ? 3 : 1;
+  return algo;
+}
+
 extern "C" {
+
+size_t b2s_conv_ws_bytes(int32_t K, int32_t c_in, int32_t c_out) {
+  return conv_tc_supported(K, c_in, c_out) ? conv_tc_ws_bytes(K, c_in, c_out) : 256;
+}
 
 int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, float* out, int64_t n_out,
                    int32_t K, int32_t c_in, int32_t c_out, int32_t w_transposed, int32_t k_reversed,
-                   int32_t algo, b2s_stream_t stream) {
+                   int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream) {
   if (n_out < 0 || K < 1 || K > 125 || c_in < 1 || c_out < 1 || (nbr == nullptr && K != 1)) {
     set_error("conv_table: invalid argument");
     return B2S_E_INVALID;
   }
-  if (algo == 2 || algo == 3) {
-    if (!conv_tc_supported(K, c_in, c_out)) {
-      set_error("conv_table: shape not supported by the tcgen05 path");
-      return B2S_E_INVALID;
-    }
-    return conv_table_tc(A, W, nbr, out, n_out, K, c_in, c_out, w_transposed, k_reversed, algo == 2 ? 3 : 1, stream);
-  }
+  int nsplit = 0;
+  algo = pick(algo, K, c_in, c_out, "conv_table", &nsplit);
+  if (algo < 0) return B2S_E_INVALID;
+  if (algo >= 2)
+    return conv_tc(A, W, nbr, nullptr, nullptr, out, n_out, 0, K, c_in, c_out, w_transposed, k_reversed, nsplit, false,
+                   ws, ws_bytes, stream);
   return conv_table_simt(A, W, nbr, out, n_out, K, c_in, c_out, w_transposed, k_reversed, stream);
 }
 
 int b2s_conv_pairs(const float* A, const float* W, const int32_t* src, const int32_t* dst,
                    const int32_t* k_offsets, float* out, int32_t K, int32_t c_in, int32_t c_out,
-                   int32_t w_transposed, int64_t max_pairs, int32_t algo, b2s_stream_t stream) {
+                   int32_t w_transposed, int64_t max_pairs, int32_t algo, void* ws, size_t ws_bytes,
+                   b2s_stream_t stream) {
   if (K < 1 || K > 125 || c_in < 1 || c_out < 1 || max_pairs < 0) {
     set_error("conv_pairs: invalid argument");
     return B2S_E_INVALID;
   }
-  (void)algo;
+  int nsplit = 0;
+  algo = pick(algo, K, c_in, c_out, "conv_pairs", &nsplit);
+  if (algo < 0) return B2S_E_INVALID;
+  if (algo >= 2)
+    return conv_tc(A, W, src, dst, k_offsets, out, 0, max_pairs, K, c_in, c_out, w_transposed, 0, nsplit, true, ws,
+                   ws_bytes, stream);
   return conv_pairs_simt(A, W, src, dst, k_offsets, out, K, c_in, c_out, w_transposed, max_pairs, stream);
 }
 

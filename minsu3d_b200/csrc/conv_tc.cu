@@ -1,9 +1,444 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM path -- placeholder until the kernel lands.
+// T3 / T4 on the 5th-generation tensor cores: output-stationary implicit GEMM with tcgen05.mma
+// (kind::tf32), accumulators in TMEM, weights staged by the TMA engine (cp.async.bulk), gathered
+// activations staged by producer warps, mbarrier pipelines between the three roles.
+//
+//   out[o, :] = sum_k in[nbr[o,k], :] @ W[k]        (appendix A.7; common.py:12,37,40,69,77)
+//
+// GEMM view per CTA: D[128 x Cout] (TMEM, fp32) += A[128 x 16] (smem) * B[16 x Cout] (smem) for every
+// "slab" = (active kernel offset k, 16-channel chunk c).  A slabs are gathered rows (zero rows where the
+// neighbour is missing); offsets with no neighbour in the whole tile are skipped.
+//
+// Precision: the reference computes in fp32.  NSPLIT = 3 runs the 3xTF32 split (x = hi + lo with
+// hi = x truncated to TF32; D += Ahi*Bhi + Ahi*Blo + Alo*Bhi), which is fp32-class (~1e-6 relative);
+// NSPLIT = 1 is plain TF32 (~5e-4 relative) for callers that accept it.
+//
+// Shared-memory operand layout: K-major, SWIZZLE_64B (a slab row is 16 fp32 = 64 bytes):
+//   byte(row r, k j) = r*64 + (((j>>2) ^ ((r>>1)&3)) << 4) + (j&3)*4        [Swizzle<2,4,3>]
+// Weights are pre-packed by pack_weights_kernel into exactly this byte image per slab, so one 1-D bulk
+// copy (UBLKCP) per slab moves them, no tensor map needed.
+#include <algorithm>
+
 #include "common.cuh"
+
 namespace b2s {
-bool conv_tc_supported(int, int, int) { return false; }
-int conv_table_tc(const float*, const float*, const int32_t*, float*, int64_t, int, int, int, int, int, int, cudaStream_t) {
-  set_error("tcgen05 path not built");
-  return B2S_E_INVALID;
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 192;  // warps 0-3: gather producers + epilogue, warp 4: MMA issuer, warp 5: weight loader
+constexpr int TC_A_SLAB = TC_BM * 64;  // bytes
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major) | SBO>>4 [32,46) = 512 B between
+// 8-row groups | version=1 [46,48) | layout_type=4 (SWIZZLE_64B) [61,64)
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
+// a/b K-major, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__host__ __device__ __forceinline__ int sw64_offset(int row, int j) {  // byte offset inside a slab
+  return row * 64 + ((((j >> 2) ^ ((row >> 1) & 3))) << 4) + (j & 3) * 4;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: W[K][c_in][c_out] (or its transpose view) -> per-slab SW64 images, hi then lo
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    pack_weights_kernel(const float* __restrict__ W, float* __restrict__ Bp, int K, int c_in, int c_out,
+                        int w_transposed, int64_t total) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int per_slab = c_out * 16;
+  int64_t slab = e / per_slab;
+  int within = (int)(e - slab * per_slab);
+  int n = within >> 4, j = within & 15;
+  int nc = c_in >> 4;
+  int k = (int)(slab / nc), c = (int)(slab - (int64_t)k * nc);
+  int ci = c * 16 + j;
+  const float* Wk = W + (int64_t)k * c_in * c_out;
+  float v = w_transposed ? Wk[(int64_t)n * c_in + ci] : Wk[(int64_t)ci * c_out + n];
+  float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  float lo = v - hi;
+  int64_t off = slab * per_slab + (sw64_offset(n, j) >> 2);
+  Bp[off] = hi;
+  Bp[total + off] = lo;
+}
+
+struct TcArgs {
+  const float* A;
+  const float* Bp;       // packed weights: [hi image | lo image], each K*(c_in/16) slabs of c_out*16 floats
+  const int32_t* idx;    // TABLE: nbr [n_out, K] (or NULL = identity, K == 1); PAIRS: src
+  const int32_t* dst;    // PAIRS: destination rows
+  const int32_t* k_offsets;
+  float* out;
+  int64_t n_out;
+  int64_t bp_half;       // floats in one image
+  int K, c_in, c_out, k_reversed, stages, tmem_cols;
+};
+
+template <bool PAIRS, int NSPLIT>
+__global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.stages;
+  const int b_slab = a.c_out * 64;                       // bytes of one weight slab image
+  const int stage_bytes = NSPLIT == 3 ? 2 * TC_A_SLAB + 2 * b_slab : TC_A_SLAB + b_slab;
+  // [stages x stage_bytes][barriers][tmem ptr][mask][index tile]
+  uint64_t* bars = (uint64_t*)(sm + (size_t)S * stage_bytes);
+  const uint32_t bar0 = base + (uint32_t)S * stage_bytes;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * S);
+  uint32_t* s_tmem = (uint32_t*)(bars + 2 * S + 1);
+  uint32_t* s_mask = s_tmem + 1;
+  int32_t* s_idx = (int32_t*)(s_tmem + 4);
+
+  // ---- tile -> rows ------------------------------------------------------------------------
+  int64_t row0 = 0;
+  int rows = 0, k_single = -1, p0 = 0;
+  const int K = a.K;
+  if (!PAIRS) {
+    row0 = (int64_t)blockIdx.x * TC_BM;
+    rows = (int)min((int64_t)TC_BM, a.n_out - row0);
+  } else {
+    int chunk = blockIdx.x, kk, begin = 0, end = 0;
+    bool found = false;
+    for (kk = 0; kk < K; ++kk) {
+      begin = a.k_offsets[kk];
+      end = a.k_offsets[kk + 1];
+      int nch = (end - begin + TC_BM - 1) / TC_BM;
+      if (chunk < nch) {
+        found = true;
+        break;
+      }
+      chunk -= nch;
+    }
+    if (!found) return;
+    k_single = kk;
+    p0 = begin + chunk * TC_BM;
+    rows = min(TC_BM, end - p0);
+  }
+
+  // ---- prologue ----------------------------------------------------------------------------
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar(s), 128 + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    *s_mask = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(smem_u32(s_tmem), (uint32_t)a.tmem_cols);
+  if (!PAIRS) {
+    if (a.idx != nullptr) {
+      const int32_t* p = a.idx + row0 * K;
+      for (int e = tid; e < rows * K; e += TC_THREADS) s_idx[e] = p[e];
+    }
+  } else {
+    for (int e = tid; e < rows; e += TC_THREADS) {
+      s_idx[e] = a.idx[p0 + e];
+      s_idx[TC_BM + e] = a.dst[p0 + e];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // active-offset mask of the tile
+  if (!PAIRS && a.idx != nullptr && warp < 4) {
+    uint32_t m = 0;
+    if (tid < rows)
+      for (int k = 0; k < K; ++k) m |= (s_idx[tid * K + k] >= 0) ? (1u << k) : 0u;
+    m = __reduce_or_sync(0xffffffffu, m);
+    if (lane == 0 && m) atomicOr(s_mask, m);
+  }
+  __syncthreads();
+  uint32_t kmask;
+  if (PAIRS) kmask = 1u << k_single;
+  else kmask = (a.idx == nullptr) ? 1u : *s_mask;
+  const uint32_t tmem_base = *s_tmem;
+  const int nc = a.c_in >> 4;
+  const int T = __popc(kmask) * nc;  // slabs of this tile
+
+  if (warp < 4) {
+    // =========================== gather producers (thread = tile row) ========================
+    // Three register slots rotate (load slab t+2 while slab t is stored): two slabs of gathered
+    // data (8 x 16 B) are in flight per thread, which is what hides the L2 latency.
+    const int r = tid;
+    uint32_t km = kmask;
+    int k = -1, c = nc;  // iterator state of the NEXT slab to load
+    const float* rowp = nullptr;
+    float4 ra[4], rb[4], rc[4];
+    auto load_next = [&](float4 (&dst)[4]) {
+      if (c == nc) {
+        k = __ffs(km) - 1;
+        km &= km - 1;
+        c = 0;
+        int g = -1;
+        if (r < rows) {
+          if (PAIRS) g = s_idx[r];
+          else g = (a.idx == nullptr) ? (int)(row0 + r) : s_idx[r * K + k];
+        }
+        rowp = g >= 0 ? a.A + (int64_t)g * a.c_in : nullptr;
+      }
+      if (rowp) {
+        const float4* p = (const float4*)(rowp + c * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = __ldg(p + q);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      ++c;
+    };
+    const int swz = (r >> 1) & 3;
+    auto store_slab = [&](int t, const float4 (&src)[4]) {
+      const int s = t % S;
+      const uint32_t ph = (uint32_t)(t / S) & 1u;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      uint8_t* a_hi = sm + (size_t)s * stage_bytes + r * 64;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 v = src[q];
+        if (NSPLIT == 3) {
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          *(float4*)(a_hi + ((q ^ swz) << 4)) = h;
+          *(float4*)(a_hi + TC_A_SLAB + ((q ^ swz) << 4)) = l;
+        } else {
+          *(float4*)(a_hi + ((q ^ swz) << 4)) = v;
+        }
+      }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(full_bar(s));
+    };
+    if (T > 0) load_next(ra);
+    if (T > 1) load_next(rb);
+    for (int t = 0; t < T; t += 3) {
+      if (t + 2 < T) load_next(rc);
+      store_slab(t, ra);
+      if (t + 3 < T) load_next(ra);
+      if (t + 1 < T) store_slab(t + 1, rb);
+      if (t + 4 < T) load_next(rb);
+      if (t + 2 < T) store_slab(t + 2, rc);
+    }
+    // =========================== epilogue (thread = TMEM lane = tile row) ====================
+    int64_t orow = -1;
+    if (r < rows) orow = PAIRS ? (int64_t)s_idx[TC_BM + r] : row0 + r;
+    if (T > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int col = 0; col < a.c_out; col += 16) {
+      uint32_t v[16];
+      if (T > 0) {
+        tmem_ld16(taddr + (uint32_t)col, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
+      }
+      if (orow >= 0) {
+        float4* o = (float4*)(a.out + orow * a.c_out + col);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          o[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                             __uint_as_float(v[4 * q + 3]));
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =========================== MMA issuer (one thread) =====================================
+    if (lane == 0 && T > 0) {
+      const uint32_t idesc = make_idesc_tf32(a.c_out);
+      for (int t = 0; t < T; ++t) {
+        const int s = t % S;
+        const uint32_t ph = (uint32_t)(t / S) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_hi = base + (uint32_t)s * stage_bytes;
+        const uint32_t b_hi = a_hi + (NSPLIT == 3 ? 2 * TC_A_SLAB : TC_A_SLAB);
+        const uint64_t da_hi = make_desc_sw64(a_hi), db_hi = make_desc_sw64(b_hi);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {  // two K=8 slices of the 16-wide slab: +32 bytes = +2 encoded
+          const uint32_t acc = (t > 0 || ks > 0) ? 1u : 0u;
+          if (NSPLIT == 3) {
+            const uint64_t da_lo = make_desc_sw64(a_hi + TC_A_SLAB), db_lo = make_desc_sw64(b_hi + b_slab);
+            umma_tf32(tmem_base, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
+            umma_tf32(tmem_base, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
+            umma_tf32(tmem_base, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+          }
+        }
+        umma_commit(empty_bar(s));  // frees the stage once the MMAs above have read it
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // =========================== weight loader (one thread, TMA engine) ======================
+    if (lane == 0 && T > 0) {
+      uint32_t km = kmask;
+      int k = -1, c = nc;
+      for (int t = 0; t < T; ++t) {
+        if (c == nc) {
+          k = __ffs(km) - 1;
+          km &= km - 1;
+          c = 0;
+        }
+        const int kw = a.k_reversed ? (K - 1 - k) : k;
+        const int s = t % S;
+        const uint32_t ph = (uint32_t)(t / S) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t b_hi = base + (uint32_t)s * stage_bytes + (NSPLIT == 3 ? 2 * TC_A_SLAB : TC_A_SLAB);
+        const float* src = a.Bp + ((int64_t)kw * nc + c) * (int64_t)(a.c_out * 16);
+        mbar_arrive_expect_tx(full_bar(s), (uint32_t)(NSPLIT == 3 ? 2 * b_slab : b_slab));
+        bulk_g2s(b_hi, src, (uint32_t)b_slab, full_bar(s));
+        if (NSPLIT == 3) bulk_g2s(b_hi + b_slab, src + a.bp_half, (uint32_t)b_slab, full_bar(s));
+        ++c;
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  }
+}
+
+bool conv_tc_supported(int K, int c_in, int c_out) {
+  return K >= 1 && K <= 32 && c_in >= 16 && (c_in % 16) == 0 && c_out >= 16 && (c_out % 16) == 0 && c_out <= 256;
+}
+
+size_t conv_tc_ws_bytes(int K, int c_in, int c_out) { return align_up((size_t)K * c_in * c_out * 4 * 2) + 256; }
+
+template <bool PAIRS, int NSPLIT>
+static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream) {
+  const int b_slab = a.c_out * 64;
+  const int stage_bytes = NSPLIT == 3 ? 2 * TC_A_SLAB + 2 * b_slab : TC_A_SLAB + b_slab;
+  const size_t fixed = 1024 /*align slack*/ + 8 * (2 * 8 + 1) + 16 + (size_t)(PAIRS ? 2 * TC_BM : TC_BM * a.K) * 4 + 64;
+  // the gather latency is hidden by register prefetch, so shared memory only buffers finished slabs:
+  // few stages -> small footprint -> 3-4 co-resident CTAs per SM
+  int stages = 3;
+  while (stages > 2 && (size_t)stages * stage_bytes + fixed > 56 * 1024) --stages;
+  a.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes + fixed;
+  int cols = 32;
+  while (cols < a.c_out) cols <<= 1;
+  a.tmem_cols = cols;
+  auto kern = conv_tc_kernel<PAIRS, NSPLIT>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<(unsigned)grid_x, TC_THREADS, smem, stream>>>(a);
+  return check_launch("conv_tc");
+}
+
+// ws: packed weights, conv_tc_ws_bytes(K, c_in, c_out) bytes
+int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* dst, const int32_t* k_offsets,
+            float* out, int64_t n_out, int64_t max_pairs, int K, int c_in, int c_out, int wT, int krev, int nsplit,
+            bool pairs, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (ws_bytes < conv_tc_ws_bytes(K, c_in, c_out)) {
+    set_error("conv_tc: workspace too small");
+    return B2S_E_WORKSPACE;
+  }
+  int64_t half = (int64_t)K * c_in * c_out;
+  float* Bp = (float*)ws;
+  pack_weights_kernel<<<(unsigned)cdiv(half, 256), 256, 0, stream>>>(W, Bp, K, c_in, c_out, wT, half);
+  TcArgs a;
+  a.A = A;
+  a.Bp = Bp;
+  a.idx = idx;
+  a.dst = dst;
+  a.k_offsets = k_offsets;
+  a.out = out;
+  a.n_out = n_out;
+  a.bp_half = half;
+  a.K = K;
+  a.c_in = c_in;
+  a.c_out = c_out;
+  a.k_reversed = krev;
+  a.stages = 0;
+  a.tmem_cols = 0;
+  if (!pairs) {
+    if (n_out == 0) return B2S_OK;
+    int64_t gx = cdiv(n_out, TC_BM);
+    return nsplit == 3 ? launch_tc<false, 3>(a, gx, stream) : launch_tc<false, 1>(a, gx, stream);
+  }
+  if (max_pairs == 0) return B2S_OK;
+  int64_t gx = cdiv(max_pairs, TC_BM) + K;
+  return nsplit == 3 ? launch_tc<true, 3>(a, gx, stream) : launch_tc<true, 1>(a, gx, stream);
+}
+
 }  // namespace b2s

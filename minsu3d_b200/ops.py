@@ -110,12 +110,18 @@ def _f32c(t, name):
     require(t.dtype == torch.float32 and t.is_contiguous(), "%s must be contiguous float32" % name)
 
 
+def _conv_ws(K, c_in, c_out, device):
+    return workspace(lib().b2s_conv_ws_bytes(K, c_in, c_out), device)
+
+
 def conv_table(A, W, nbr, n_out, K, c_in, c_out, w_transposed=False, k_reversed=False, algo=None):
     _f32c(A, "A")
     _f32c(W, "W")
     out = torch.empty((n_out, c_out), dtype=torch.float32, device=A.device)
+    ws = _conv_ws(K, c_in, c_out, A.device)
     check(lib().b2s_conv_table(ptr(A), ptr(W), ptr(nbr), ptr(out), n_out, K, c_in, c_out, int(w_transposed),
-                               int(k_reversed), _default_algo if algo is None else algo, stream()), "conv_table")
+                               int(k_reversed), _default_algo if algo is None else algo, ptr(ws), ws.numel(),
+                               stream()), "conv_table")
     return out
 
 
@@ -125,9 +131,10 @@ def conv_pairs(A, W, src, dst, k_offsets, n_out, K, c_in, c_out, max_pairs, w_tr
     _f32c(W, "W")
     alloc = torch.zeros if zero_init else torch.empty
     out = alloc((n_out, c_out), dtype=torch.float32, device=A.device)
+    ws = _conv_ws(K, c_in, c_out, A.device)
     check(lib().b2s_conv_pairs(ptr(A), ptr(W), ptr(src), ptr(dst), ptr(k_offsets), ptr(out), K, c_in, c_out,
                                int(w_transposed), int(max_pairs), _default_algo if algo is None else algo,
-                               stream()), "conv_pairs")
+                               ptr(ws), ws.numel(), stream()), "conv_pairs")
     return out
 
 
@@ -143,14 +150,16 @@ def conv_wgrad(A, G, src, dst, k_offsets, K, c_a, c_g, max_pairs, algo=None):
 # ------------------------------------------------------------------------------------------
 # T5 batch norm
 # ------------------------------------------------------------------------------------------
-def bn_stats(x):
+def bn_stats(x, eps=1e-5, momentum=0.0, running_mean=None, running_var=None):
+    """Batch statistics in one call: returns (mean, rstd); updates the running statistics in place."""
     _f32c(x, "x")
     n, c = x.shape
     mean = torch.empty(c, dtype=torch.float32, device=x.device)
-    var = torch.empty(c, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(c, dtype=torch.float32, device=x.device)
     ws = workspace(lib().b2s_bn_ws_bytes(n, c), x.device)
-    check(lib().b2s_bn_stats(ptr(x), n, c, 0.0, ptr(mean), ptr(var), ptr(ws), ws.numel(), stream()), "bn_stats")
-    return mean, var
+    check(lib().b2s_bn_stats(ptr(x), n, c, float(eps), float(momentum), ptr(running_mean), ptr(running_var),
+                             ptr(mean), None, ptr(rstd), ptr(ws), ws.numel(), stream()), "bn_stats")
+    return mean, rstd
 
 
 def bn_apply(x, mean, rstd, gamma, beta, relu, out=None):
