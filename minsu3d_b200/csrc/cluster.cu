@@ -451,12 +451,27 @@ __global__ void __launch_bounds__(128)
 }
 
 static int coop_grid(const void* kernel, int threads, int64_t work_items) {
-  int dev = 0, sms = B2S_SM_COUNT, per_sm = 1;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
-  if (per_sm < 1) per_sm = 1;
-  int g = sms * std::min(per_sm, 2);
+  // device / occupancy queries cost ~40 us each: cache them per kernel (one process drives one GPU)
+  static const void* cached_kernel[4] = {nullptr, nullptr, nullptr, nullptr};
+  static int cached_blocks[4] = {0, 0, 0, 0};
+  int max_blocks = 0;
+  for (int i = 0; i < 4; ++i)
+    if (cached_kernel[i] == kernel) max_blocks = cached_blocks[i];
+  if (max_blocks == 0) {
+    int dev = 0, sms = B2S_SM_COUNT, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    if (per_sm < 1) per_sm = 1;
+    max_blocks = sms * std::min(per_sm, 2);
+    for (int i = 0; i < 4; ++i)
+      if (cached_kernel[i] == nullptr) {
+        cached_kernel[i] = kernel;
+        cached_blocks[i] = max_blocks;
+        break;
+      }
+  }
+  int g = max_blocks;
   int64_t want = cdiv(work_items, threads);
   if (want < 1) want = 1;
   if (want < g) g = (int)want;

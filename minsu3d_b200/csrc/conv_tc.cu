@@ -4,19 +4,25 @@
 //
 //   out[o, :] = sum_k in[nbr[o,k], :] @ W[k]        (appendix A.7; common.py:12,37,40,69,77)
 //
-// GEMM view per CTA: D[128 x Cout] (TMEM, fp32) += A[128 x 16] (smem) * B[16 x Cout] (smem) for every
+// GEMM view per CTA: D[128 x Cout] (TMEM, fp32) += A[128 x 16] (TMEM) * B[16 x Cout] (smem) for every
 // "slab" = (active kernel offset k, 16-channel chunk c).  A slabs are gathered rows (zero rows where the
-// neighbour is missing); offsets with no neighbour in the whole tile are skipped.
+// neighbour is missing); offsets with no neighbour in the whole tile are skipped.  The gathered A operand
+// is written straight from registers into TENSOR MEMORY (tcgen05.st) and consumed by the TS form of
+// tcgen05.mma: the first version staged A in shared memory and was bound by shared-memory bandwidth
+// (ncu: LSU + tensor-core smem wavefronts at 97 %, profiles/r01_conv_tc_smem_bound.txt) because the
+// 3xTF32 split re-reads every operand three times; with A in TMEM only the small weight tile is read
+// from shared memory.
 //
 // Precision: the reference computes in fp32.  NSPLIT = 3 runs the 3xTF32 split (x = hi + lo with
 // hi = x truncated to TF32; D += Ahi*Bhi + Ahi*Blo + Alo*Bhi), which is fp32-class (~1e-6 relative);
 // NSPLIT = 1 is plain TF32 (~5e-4 relative) for callers that accept it.
 //
-// Shared-memory operand layout: K-major, SWIZZLE_64B (a slab row is 16 fp32 = 64 bytes):
+// Shared-memory layout of the B (weight) operand: K-major, SWIZZLE_64B (a slab row is 16 fp32 = 64 bytes):
 //   byte(row r, k j) = r*64 + (((j>>2) ^ ((r>>1)&3)) << 4) + (j&3)*4        [Swizzle<2,4,3>]
 // Weights are pre-packed by pack_weights_kernel into exactly this byte image per slab, so one 1-D bulk
 // copy (UBLKCP) per slab moves them, no tensor map needed.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -76,6 +82,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
       : "memory");
 }
+// TS form: A operand from tensor memory (lane = tile row, 8 consecutive 32-bit columns per K = 8 slice)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -137,7 +160,7 @@ struct TcArgs {
   float* out;
   int64_t n_out;
   int64_t bp_half;       // floats in one image
-  int K, c_in, c_out, k_reversed, stages, tmem_cols;
+  int K, c_in, c_out, k_reversed, stages, tmem_cols, a_col0;
 };
 
 template <bool PAIRS, int NSPLIT>
@@ -148,9 +171,12 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
   uint8_t* sm = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.stages;
-  const int b_slab = a.c_out * 64;                       // bytes of one weight slab image
-  const int stage_bytes = NSPLIT == 3 ? 2 * TC_A_SLAB + 2 * b_slab : TC_A_SLAB + b_slab;
-  // [stages x stage_bytes][barriers][tmem ptr][mask][index tile]
+  constexpr int NB = NSPLIT == 3 ? 2 : 1;        // weight images per slab (hi, lo)
+  constexpr int A_COLS = NSPLIT == 3 ? 32 : 16;  // tensor-memory columns of one A stage (hi, lo)
+  const int b_slab = a.c_out * 64;               // bytes of one weight slab image
+  const int stage_bytes = NB * b_slab;
+  // shared memory: [stages x weight slab(s)][barriers][tmem ptr][mask][index tile]
+  // tensor memory: [accumulator: c_out columns][stages x A_COLS columns of the gathered A operand]
   uint64_t* bars = (uint64_t*)(sm + (size_t)S * stage_bytes);
   const uint32_t bar0 = base + (uint32_t)S * stage_bytes;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -200,7 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
   if (!PAIRS) {
     if (a.idx != nullptr) {
       const int32_t* p = a.idx + row0 * K;
-      for (int e = tid; e < rows * K; e += TC_THREADS) s_idx[e] = p[e];
+      for (int e = tid; e < rows * K; e += TC_THREADS) s_idx[e] = __ldg(p + e);
     }
   } else {
     for (int e = tid; e < rows; e += TC_THREADS) {
@@ -228,17 +254,17 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
   const int T = __popc(kmask) * nc;  // slabs of this tile
 
   if (warp < 4) {
-    // =========================== gather producers (thread = tile row) ========================
-    // Three register slots rotate (load slab t+2 while slab t is stored): two slabs of gathered
-    // data (8 x 16 B) are in flight per thread, which is what hides the L2 latency.
+    // =========================== gather producers (thread = tile row = TMEM lane) ============
+    // Three register slots rotate (slab t+2 is loaded while slab t is written to tensor memory): two
+    // slabs of gathered data (8 x 16 B per thread) are in flight.
     const int r = tid;
     uint32_t km = kmask;
-    int k = -1, c = nc;  // iterator state of the NEXT slab to load
+    int c = nc;  // iterator state of the NEXT slab to load
     const float* rowp = nullptr;
     float4 ra[4], rb[4], rc[4];
     auto load_next = [&](float4 (&dst)[4]) {
       if (c == nc) {
-        k = __ffs(km) - 1;
+        const int k = __ffs(km) - 1;
         km &= km - 1;
         c = 0;
         int g = -1;
@@ -258,40 +284,47 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
       }
       ++c;
     };
-    const int swz = (r >> 1) & 3;
-    auto store_slab = [&](int t, const float4 (&src)[4]) {
-      const int s = t % S;
-      const uint32_t ph = (uint32_t)(t / S) & 1u;
-      mbar_wait(empty_bar(s), ph ^ 1u);
-      uint8_t* a_hi = sm + (size_t)s * stage_bytes + r * 64;
+    const uint32_t a_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a.a_col0;
+    int st_s = 0;        // stage of the next slab to store
+    uint32_t st_ph = 0;  // its phase bit
+    auto store_slab = [&](const float4 (&src)[4]) {
+      mbar_wait(empty_bar(st_s), st_ph ^ 1u);
+      tc_fence_after();
+      uint32_t hi[16], lo[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float4 v = src[q];
-        if (NSPLIT == 3) {
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          *(float4*)(a_hi + ((q ^ swz) << 4)) = h;
-          *(float4*)(a_hi + TC_A_SLAB + ((q ^ swz) << 4)) = l;
-        } else {
-          *(float4*)(a_hi + ((q ^ swz) << 4)) = v;
+        const float v[4] = {src[q].x, src[q].y, src[q].z, src[q].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (NSPLIT == 3) {
+            uint32_t h = __float_as_uint(v[j]) & 0xFFFFE000u;
+            hi[4 * q + j] = h;
+            lo[4 * q + j] = __float_as_uint(v[j] - __uint_as_float(h));
+          } else {
+            hi[4 * q + j] = __float_as_uint(v[j]);
+          }
         }
       }
-      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(full_bar(s));
+      const uint32_t col = a_lane + (uint32_t)(st_s * A_COLS);
+      tmem_st16(col, hi);
+      if (NSPLIT == 3) tmem_st16(col + 16, lo);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(full_bar(st_s));
+      if (++st_s == S) {
+        st_s = 0;
+        st_ph ^= 1u;
+      }
     };
     if (T > 0) load_next(ra);
     if (T > 1) load_next(rb);
     for (int t = 0; t < T; t += 3) {
       if (t + 2 < T) load_next(rc);
-      store_slab(t, ra);
+      store_slab(ra);
       if (t + 3 < T) load_next(ra);
-      if (t + 1 < T) store_slab(t + 1, rb);
+      if (t + 1 < T) store_slab(rb);
       if (t + 4 < T) load_next(rb);
-      if (t + 2 < T) store_slab(t + 2, rc);
+      if (t + 2 < T) store_slab(rc);
     }
     // =========================== epilogue (thread = TMEM lane = tile row) ====================
     int64_t orow = -1;
@@ -322,27 +355,31 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
     // =========================== MMA issuer (one thread) =====================================
     if (lane == 0 && T > 0) {
       const uint32_t idesc = make_idesc_tf32(a.c_out);
+      int s = 0;
+      uint32_t ph = 0;
       for (int t = 0; t < T; ++t) {
-        const int s = t % S;
-        const uint32_t ph = (uint32_t)(t / S) & 1u;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t a_hi = base + (uint32_t)s * stage_bytes;
-        const uint32_t b_hi = a_hi + (NSPLIT == 3 ? 2 * TC_A_SLAB : TC_A_SLAB);
-        const uint64_t da_hi = make_desc_sw64(a_hi), db_hi = make_desc_sw64(b_hi);
+        const uint32_t b_hi = base + (uint32_t)s * stage_bytes;
+        const uint64_t db_hi = make_desc_sw64(b_hi);
+        const uint32_t ta_hi = tmem_base + (uint32_t)a.a_col0 + (uint32_t)(s * A_COLS);
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {  // two K=8 slices of the 16-wide slab: +32 bytes = +2 encoded
+        for (int ks = 0; ks < 2; ++ks) {  // two K = 8 slices: +8 TMEM columns (A), +32 bytes = +2 encoded (B)
           const uint32_t acc = (t > 0 || ks > 0) ? 1u : 0u;
           if (NSPLIT == 3) {
-            const uint64_t da_lo = make_desc_sw64(a_hi + TC_A_SLAB), db_lo = make_desc_sw64(b_hi + b_slab);
-            umma_tf32(tmem_base, da_lo + 2 * ks, db_hi + 2 * ks, idesc, acc);
-            umma_tf32(tmem_base, da_hi + 2 * ks, db_lo + 2 * ks, idesc, 1u);
-            umma_tf32(tmem_base, da_hi + 2 * ks, db_hi + 2 * ks, idesc, 1u);
+            const uint64_t db_lo = make_desc_sw64(b_hi + b_slab);
+            umma_tf32_ts(tmem_base, ta_hi + 16 + 8 * ks, db_hi + 2 * ks, idesc, acc);  // lo * hi
+            umma_tf32_ts(tmem_base, ta_hi + 8 * ks, db_lo + 2 * ks, idesc, 1u);         // hi * lo
+            umma_tf32_ts(tmem_base, ta_hi + 8 * ks, db_hi + 2 * ks, idesc, 1u);         // hi * hi
           } else {
-            umma_tf32(tmem_base, da_hi + 2 * ks, db_hi + 2 * ks, idesc, acc);
+            umma_tf32_ts(tmem_base, ta_hi + 8 * ks, db_hi + 2 * ks, idesc, acc);
           }
         }
         umma_commit(empty_bar(s));  // frees the stage once the MMAs above have read it
+        if (++s == S) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
       umma_commit(tmem_full_bar);
     }
@@ -351,7 +388,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
     // =========================== weight loader (one thread, TMA engine) ======================
     if (lane == 0 && T > 0) {
       uint32_t km = kmask;
-      int k = -1, c = nc;
+      int k = -1, c = nc, s = 0;
+      uint32_t ph = 0;
       for (int t = 0; t < T; ++t) {
         if (c == nc) {
           k = __ffs(km) - 1;
@@ -359,15 +397,17 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
           c = 0;
         }
         const int kw = a.k_reversed ? (K - 1 - k) : k;
-        const int s = t % S;
-        const uint32_t ph = (uint32_t)(t / S) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t b_hi = base + (uint32_t)s * stage_bytes + (NSPLIT == 3 ? 2 * TC_A_SLAB : TC_A_SLAB);
+        const uint32_t b_hi = base + (uint32_t)s * stage_bytes;
         const float* src = a.Bp + ((int64_t)kw * nc + c) * (int64_t)(a.c_out * 16);
-        mbar_arrive_expect_tx(full_bar(s), (uint32_t)(NSPLIT == 3 ? 2 * b_slab : b_slab));
+        mbar_arrive_expect_tx(full_bar(s), (uint32_t)(NB * b_slab));
         bulk_g2s(b_hi, src, (uint32_t)b_slab, full_bar(s));
         if (NSPLIT == 3) bulk_g2s(b_hi + b_slab, src + a.bp_half, (uint32_t)b_slab, full_bar(s));
         ++c;
+        if (++s == S) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
     __syncwarp();
@@ -387,20 +427,25 @@ size_t conv_tc_ws_bytes(int K, int c_in, int c_out) { return align_up((size_t)K 
 
 template <bool PAIRS, int NSPLIT>
 static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream) {
-  const int b_slab = a.c_out * 64;
-  const int stage_bytes = NSPLIT == 3 ? 2 * TC_A_SLAB + 2 * b_slab : TC_A_SLAB + b_slab;
-  const size_t fixed = 1024 /*align slack*/ + 8 * (2 * 8 + 1) + 16 + (size_t)(PAIRS ? 2 * TC_BM : TC_BM * a.K) * 4 + 64;
-  // the gather latency is hidden by register prefetch, so shared memory only buffers finished slabs:
-  // few stages -> small footprint -> 3-4 co-resident CTAs per SM
-  int stages = 3;
-  while (stages > 2 && (size_t)stages * stage_bytes + fixed > 56 * 1024) --stages;
+  auto bucket = [](int c) { int b = 32; while (b < c) b <<= 1; return b; };
+  const int stage_bytes = (NSPLIT == 3 ? 2 : 1) * a.c_out * 64;
+  const int a_cols = NSPLIT == 3 ? 32 : 16;
+  // as many stages as the tensor-memory bucket of (accumulator + 2 stages) holds, at most 6, within ~64 KB smem
+  int stages = 6;
+  while (stages > 2 && (bucket(a.c_out + stages * a_cols) > bucket(a.c_out + 2 * a_cols) ||
+                        (size_t)stages * stage_bytes > 64 * 1024))
+    --stages;
   a.stages = stages;
+  a.a_col0 = a.c_out;
+  a.tmem_cols = bucket(a.c_out + stages * a_cols);
+  const size_t fixed = 1024 /*align slack*/ + 8 * (2 * 8 + 1) + 16 + (size_t)(PAIRS ? 2 * TC_BM : TC_BM * a.K) * 4 + 64;
   size_t smem = (size_t)stages * stage_bytes + fixed;
-  int cols = 32;
-  while (cols < a.c_out) cols <<= 1;
-  a.tmem_cols = cols;
   auto kern = conv_tc_kernel<PAIRS, NSPLIT>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
   kern<<<(unsigned)grid_x, TC_THREADS, smem, stream>>>(a);
   return check_launch("conv_tc");
 }
@@ -413,6 +458,7 @@ int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* d
     set_error("conv_tc: workspace too small");
     return B2S_E_WORKSPACE;
   }
+  if ((!pairs && n_out == 0) || (pairs && max_pairs == 0)) return B2S_OK;
   int64_t half = (int64_t)K * c_in * c_out;
   float* Bp = (float*)ws;
   pack_weights_kernel<<<(unsigned)cdiv(half, 256), 256, 0, stream>>>(W, Bp, K, c_in, c_out, wT, half);
@@ -429,14 +475,11 @@ int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* d
   a.c_in = c_in;
   a.c_out = c_out;
   a.k_reversed = krev;
-  a.stages = 0;
-  a.tmem_cols = 0;
+  a.stages = a.tmem_cols = a.a_col0 = 0;
   if (!pairs) {
-    if (n_out == 0) return B2S_OK;
     int64_t gx = cdiv(n_out, TC_BM);
     return nsplit == 3 ? launch_tc<false, 3>(a, gx, stream) : launch_tc<false, 1>(a, gx, stream);
   }
-  if (max_pairs == 0) return B2S_OK;
   int64_t gx = cdiv(max_pairs, TC_BM) + K;
   return nsplit == 3 ? launch_tc<true, 3>(a, gx, stream) : launch_tc<true, 1>(a, gx, stream);
 }
