@@ -43,16 +43,85 @@ constexpr int CL_THREADS = 256;
 // ------------------------------------------------------------------------------------------
 // (1) membership labels
 // ------------------------------------------------------------------------------------------
+// (1a) Union-find over the SYMMETRIC edges.  Nodes joined by edges present in both directions are
+// mutually reachable, hence share m(v); contracting them first (ECL-CC style hooking: one pass over
+// the edges, no device-wide barrier, independent of the graph diameter) leaves the directed fixpoint
+// iteration below with nothing to do unless ball-query lists were truncated at 1000 neighbours.
+// An edge u->w is symmetric iff u is in list(w); the distance predicate is symmetric, so that can
+// only fail when list(w) hit the cap, in which case list(w) (ascending) is binary-searched.
+constexpr int BQ_LIST_CAP = 1000;
+
+__device__ __forceinline__ int uf_find(int32_t* parent, int v) {
+  int p = __ldcg(parent + v);
+  while (p != v) {
+    int gp = __ldcg(parent + p);
+    if (gp != p) parent[v] = gp;  // path halving (values only decrease: benign race)
+    v = p;
+    p = gp;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(256) cc_init_kernel(int n, int32_t* __restrict__ parent) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) parent[v] = v;
+}
+
+__global__ void __launch_bounds__(256)
+    cc_hook_kernel(const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ start_len,
+                   const int16_t* __restrict__ labels, int n, int32_t* parent) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= n) return;
+  const int s = __ldg(start_len + 2 * u), l = __ldg(start_len + 2 * u + 1);
+  const int lab = labels ? labels[u] : 0;
+  for (int e = lane; e < l; e += 32) {
+    const int w = __ldg(nbr_idx + s + e);
+    if (w <= u) continue;  // each undirected pair is handled from its lower endpoint
+    if (labels && labels[w] != lab) continue;
+    const int lw = __ldg(start_len + 2 * w + 1);
+    if (lw >= BQ_LIST_CAP) {  // list(w) may be truncated: is u really in it?
+      const int32_t* lst = nbr_idx + __ldg(start_len + 2 * w);
+      int lo = 0, hi = lw;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(lst + mid) < u) lo = mid + 1; else hi = mid;
+      }
+      if (lo >= lw || __ldg(lst + lo) != u) continue;
+    }
+    int ru = uf_find(parent, u), rw = uf_find(parent, w);
+    while (ru != rw) {
+      const int hi = max(ru, rw), lo = min(ru, rw);
+      const int old = atomicCAS(parent + hi, hi, lo);
+      if (old == hi) break;
+      ru = uf_find(parent, old);
+      rw = lo;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cc_compress_kernel(int n, int32_t* parent) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) {
+    int r = v, p = __ldcg(parent + r);
+    while (p != r) {
+      r = p;
+      p = __ldcg(parent + r);
+    }
+    parent[v] = r;
+  }
+}
+
+// (1b) directed fixpoint
 __global__ void __launch_bounds__(CL_THREADS)
     cc_label_kernel(const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ start_len,
                     const int16_t* __restrict__ labels, int n, int32_t* comp, unsigned* bar,
                     int* flags) {
+  // comp arrives initialised with the union-find roots of the symmetric sub-graph (cc_hook_kernel)
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int gwarp = gtid >> 5, nwarps = nthreads >> 5;
-  for (int v = gtid; v < n; v += nthreads) comp[v] = v;
-  grid_sync(bar, gridDim.x);
   int it = 0;
   while (true) {
     int* flag = flags + (it & 1);
@@ -505,6 +574,9 @@ int b2s_cluster_label(const int32_t* nbr_idx, const int32_t* start_len, const in
   }
   int* flags = (int*)(bar + 2);
   cudaMemsetAsync(bar, 0, 64 * 4, stream);
+  cc_init_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>((int)n, comp);
+  cc_hook_kernel<<<(unsigned)cdiv(n * 32, 256), 256, 0, stream>>>(nbr_idx, start_len, labels, (int)n, comp);
+  cc_compress_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>((int)n, comp);
   int grid = coop_grid((const void*)cc_label_kernel, CL_THREADS, n * 32);
   int ni = (int)n;
   void* args[] = {(void*)&nbr_idx, (void*)&start_len, (void*)&labels, (void*)&ni, (void*)&comp, (void*)&bar, (void*)&flags};

@@ -168,10 +168,9 @@ __global__ void __launch_bounds__(IG_THREADS)
 // weight gradient: gW[k][a][g] = sum over pairs of offset k of A[src][a] * G[dst][g]
 // persistent CTAs walk contiguous runs of 64-pair chunks; BA x BG channel tile per CTA.
 // ------------------------------------------------------------------------------------------
-constexpr int WG_PC = 64;  // pairs per chunk
 constexpr int WG_THREADS = 256;
 
-template <int BA, int BG, int TA, int TG>
+template <int BA, int BG, int TA, int TG, int WG_PC>
 __global__ void __launch_bounds__(WG_THREADS)
     conv_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ G,
                       const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
@@ -235,18 +234,33 @@ __global__ void __launch_bounds__(WG_THREADS)
     }
     int p0 = s_koff[k] + (ch - s_cum[k]) * WG_PC;
     int np = min(WG_PC, s_koff[k + 1] - p0);
-    // stage gathered rows (coalesced along channels)
-    for (int e = tid; e < WG_PC * BA; e += WG_THREADS) {
-      int p = e / BA, c = e - p * BA;
-      float v = 0.f;
-      if (p < np && a0 + c < c_a) v = __ldg(A + (int64_t)__ldg(src + p0 + p) * c_a + a0 + c);
-      As[p][c] = v;
-    }
-    for (int e = tid; e < WG_PC * BG; e += WG_THREADS) {
-      int p = e / BG, c = e - p * BG;
-      float v = 0.f;
-      if (p < np && g0 + c < c_g) v = __ldg(G + (int64_t)__ldg(dst + p0 + p) * c_g + g0 + c);
-      Gs[p][c] = v;
+    // stage gathered rows: one 16-byte load per thread and step, rows coalesced along channels
+    if (((c_a | c_g) & 3) == 0) {
+      for (int e = tid; e < WG_PC * (BA / 4); e += WG_THREADS) {
+        int p = e / (BA / 4), c = (e - p * (BA / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < np && a0 + c < c_a) v = __ldg((const float4*)(A + (int64_t)__ldg(src + p0 + p) * c_a + a0 + c));
+        *(float4*)&As[p][c] = v;
+      }
+      for (int e = tid; e < WG_PC * (BG / 4); e += WG_THREADS) {
+        int p = e / (BG / 4), c = (e - p * (BG / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < np && g0 + c < c_g) v = __ldg((const float4*)(G + (int64_t)__ldg(dst + p0 + p) * c_g + g0 + c));
+        *(float4*)&Gs[p][c] = v;
+      }
+    } else {
+      for (int e = tid; e < WG_PC * BA; e += WG_THREADS) {
+        int p = e / BA, c = e - p * BA;
+        float v = 0.f;
+        if (p < np && a0 + c < c_a) v = __ldg(A + (int64_t)__ldg(src + p0 + p) * c_a + a0 + c);
+        As[p][c] = v;
+      }
+      for (int e = tid; e < WG_PC * BG; e += WG_THREADS) {
+        int p = e / BG, c = e - p * BG;
+        float v = 0.f;
+        if (p < np && g0 + c < c_g) v = __ldg(G + (int64_t)__ldg(dst + p0 + p) * c_g + g0 + c);
+        Gs[p][c] = v;
+      }
     }
     __syncthreads();
     for (int p = grp; p < np; p += NG) {
@@ -302,17 +316,17 @@ int conv_wgrad_simt(const float* A, const float* G, const int32_t* src, const in
                     cudaStream_t stream) {
   cudaMemsetAsync(gW, 0, (size_t)K * c_a * c_g * 4, stream);
   if (max_pairs == 0) return check_launch("conv_wgrad(empty)");
-  int64_t chunks = cdiv(max_pairs, WG_PC) + K;
+  int64_t chunks = cdiv(max_pairs, 64) + K;
   if (c_a <= 16 && c_g <= 16) {
     int gx = (int)std::min<int64_t>(chunks, 4 * B2S_SM_COUNT);
-    conv_wgrad_kernel<16, 16, 2, 2><<<dim3(gx, 1, 1), WG_THREADS, 0, stream>>>(A, G, src, dst, k_offsets, gW, K, c_a, c_g);
+    conv_wgrad_kernel<16, 16, 4, 4, 128><<<dim3(gx, 1, 1), WG_THREADS, 0, stream>>>(A, G, src, dst, k_offsets, gW, K, c_a, c_g);
   } else if (c_a <= 32 && c_g <= 32) {
     int gx = (int)std::min<int64_t>(chunks, 4 * B2S_SM_COUNT);
-    conv_wgrad_kernel<32, 32, 2, 2><<<dim3(gx, 1, 1), WG_THREADS, 0, stream>>>(A, G, src, dst, k_offsets, gW, K, c_a, c_g);
+    conv_wgrad_kernel<32, 32, 4, 4, 128><<<dim3(gx, 1, 1), WG_THREADS, 0, stream>>>(A, G, src, dst, k_offsets, gW, K, c_a, c_g);
   } else {
     int ty = (int)cdiv(c_a, 64), tz = (int)cdiv(c_g, 64);
     int gx = (int)std::min<int64_t>(chunks, std::max(1, 4 * B2S_SM_COUNT / (ty * tz)));
-    conv_wgrad_kernel<64, 64, 4, 4><<<dim3(gx, ty, tz), WG_THREADS, 0, stream>>>(A, G, src, dst, k_offsets, gW, K, c_a, c_g);
+    conv_wgrad_kernel<64, 64, 4, 4, 64><<<dim3(gx, ty, tz), WG_THREADS, 0, stream>>>(A, G, src, dst, k_offsets, gW, K, c_a, c_g);
   }
   return check_launch("conv_wgrad");
 }

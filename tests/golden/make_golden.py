@@ -53,8 +53,8 @@ def cpu_goldens(ref):
     ci, co = E(), E()
     ref.pg_bfs_cluster(t(lab), t(idx), t(sl), ci, co, 6, 2)
     out.update(kat_idx=idx, kat_sl=sl, kat_lab=lab, kat_ci=ci.numpy().copy(), kat_co=co.numpy().copy())
-    for tag, n, collapse in (("sparse", 6000, False), ("dense", 4000, True)):
-        xyz, lab, bidx, offs = clustered_points(rng, n, n_obj=6, collapse=collapse)
+    for tag, n, n_obj, collapse in (("sparse", 6000, 6, False), ("dense", 9000, 2, True)):
+        xyz, lab, bidx, offs = clustered_points(rng, n, n_obj=n_obj, collapse=collapse)
         lab = lab.copy()
         lab[rng.integers(0, lab.size, lab.size // 25)] = 9
         idx, sl = brute_ballquery(xyz, bidx, offs, 0.03)
