@@ -48,7 +48,8 @@ constexpr int CL_THREADS = 256;
 // the edges, no device-wide barrier, independent of the graph diameter) leaves the directed fixpoint
 // iteration below with nothing to do unless ball-query lists were truncated at 1000 neighbours.
 // An edge u->w is symmetric iff u is in list(w); the distance predicate is symmetric, so that can
-// only fail when list(w) hit the cap, in which case list(w) (ascending) is binary-searched.
+// only fail when list(w) hit the cap; a capped list keeps the lowest indices, so one comparison with
+// its last element decides.
 constexpr int BQ_LIST_CAP = 1000;
 
 __device__ __forceinline__ int uf_find(int32_t* parent, int v) {
@@ -80,14 +81,10 @@ __global__ void __launch_bounds__(256)
     if (w <= u) continue;  // each undirected pair is handled from its lower endpoint
     if (labels && labels[w] != lab) continue;
     const int lw = __ldg(start_len + 2 * w + 1);
-    if (lw >= BQ_LIST_CAP) {  // list(w) may be truncated: is u really in it?
-      const int32_t* lst = nbr_idx + __ldg(start_len + 2 * w);
-      int lo = 0, hi = lw;
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(lst + mid) < u) lo = mid + 1; else hi = mid;
-      }
-      if (lo >= lw || __ldg(lst + lo) != u) continue;
+    if (lw >= BQ_LIST_CAP) {
+      // list(w) holds the LOWEST 1000 in-radius indices, and u is in radius of w (the predicate is
+      // symmetric), so u is listed iff it does not exceed the last (largest) listed index
+      if (u > __ldg(nbr_idx + __ldg(start_len + 2 * w) + lw - 1)) continue;
     }
     int ru = uf_find(parent, u), rw = uf_find(parent, w);
     while (ru != rw) {
