@@ -131,7 +131,13 @@ def ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+    """Raw cudaStream_t of torch's current stream on the current device (fast path: ~0.3 us)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -140,7 +146,7 @@ _WS = {}
 
 def workspace(nbytes, device):
     """Grow-only scratch buffer per (device, stream); stream-ordered reuse is safe."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream())
+    key = (device.index, stream())
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

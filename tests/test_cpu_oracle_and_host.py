@@ -70,6 +70,24 @@ def test_oracle_matches_reference_binary_live(ref_ops):
     assert np.array_equal(ci.numpy(), o_ci) and np.array_equal(co.numpy(), o_co)
 
 
+def test_oracle_matches_reference_cuda_kernel_goldens():
+    """tests/golden/common_ops_gpu.npz = outputs of the reference's own CUDA kernels on a B200 (make_golden.py --gpu)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "common_ops_gpu.npz"))
+    idx, sl = oracle.ballquery(g["bq_xyz"], g["bq_bidx"], g["bq_offs"], 0.03)
+    assert np.array_equal(sl[:, 1], g["bq_len"]) and np.array_equal(idx, g["bq_idx"])
+    for kind in ("mean", "min", "max"):
+        assert np.array_equal(oracle.sec(kind, g["seg_x"], g["seg_offs"]), g["sec_" + kind]), kind
+    out, arg = oracle.roipool_fp(g["seg_x"], g["seg_offs"])
+    assert np.array_equal(out, g["roipool_out"]) and np.array_equal(arg, g["roipool_arg"])
+    assert np.array_equal(oracle.gap_fp(g["seg_x"], g["seg_offs"]), g["gap"])
+    iou = oracle.get_iou(g["iou_pidx"], g["iou_poff"], g["iou_inst"], g["iou_inst_num"])
+    assert np.array_equal(iou, g["iou"])
+    iou_p = oracle.get_iou(g["iou_pidx"], g["iou_poff"], g["iou_inst"], g["iou_inst_num"], g["iou_scores"])
+    assert np.array_equal(iou_p, g["iou_pred"])
+    ml, mm = oracle.get_mask_label(g["iou_pidx"], g["iou_poff"], g["iou_inst"], g["iou_cls"], iou, -1, 0.25)
+    assert np.array_equal(ml, g["mask_label"]) and np.array_equal(mm, g["mask_label_mask"])
+
+
 # ------------------------------------------------------------------------------------------------
 # MinkowskiEngine restatement: C oracle vs dictionary restatement vs dense torch conv3d
 # ------------------------------------------------------------------------------------------------
