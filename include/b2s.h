@@ -229,6 +229,13 @@ int b2s_get_mask_label(const int32_t* proposals_idx, const int32_t* proposals_of
                        int32_t ignored_label, float iou_thr, uint8_t* mask_label,
                        uint8_t* mask_label_mask, b2s_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Diagnostics: SM-clock timeline of CTA 0 of the last tcgen05 convolution launched with the
+ * environment variable B2S_TC_DEBUG=16 (producer wait/arrive, MMA wake/commit per slab).
+ * host_out: int64 [4][256] in HOST memory.  Used only by profiling scripts.
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_debug_tc_timeline(long long* host_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "b2s_global_avg_pool_bp": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
     "b2s_get_iou": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, _P]),
     "b2s_get_mask_label": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_f32, _P, _P, _P]),
+    "b2s_debug_tc_timeline": (c_i32, [_P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -151,6 +151,9 @@ __global__ void __launch_bounds__(256)
   Bp[total + off] = lo;
 }
 
+// timeline instrumentation for CTA 0 (flag 16 of B2S_TC_DEBUG): [role][slab] SM clock
+__device__ long long g_tc_debug[4][256];
+
 struct TcArgs {
   const float* A;
   const float* Bp;       // packed weights: [hi image | lo image], each K*(c_in/16) slabs of c_out*16 floats
@@ -161,6 +164,8 @@ struct TcArgs {
   int64_t n_out;
   int64_t bp_half;       // floats in one image
   int K, c_in, c_out, k_reversed, stages, tmem_cols, a_col0;
+  int flags;  // ablation switches (env B2S_TC_DEBUG): 4 = no gathered loads, 8 = no MMA issue
+  int sb;  // weight-slab ring depth (shared memory), decoupled from the A stages (tensor memory)
 };
 
 template <bool PAIRS, int NSPLIT>
@@ -170,21 +175,26 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = a.stages;
+  const int S = a.stages, SB = a.sb;
   constexpr int NB = NSPLIT == 3 ? 2 : 1;        // weight images per slab (hi, lo)
   constexpr int A_COLS = NSPLIT == 3 ? 32 : 16;  // tensor-memory columns of one A stage (hi, lo)
   const int b_slab = a.c_out * 64;               // bytes of one weight slab image
-  const int stage_bytes = NB * b_slab;
-  // shared memory: [stages x weight slab(s)][barriers][tmem ptr][mask][index tile]
-  // tensor memory: [accumulator: c_out columns][stages x A_COLS columns of the gathered A operand]
-  uint64_t* bars = (uint64_t*)(sm + (size_t)S * stage_bytes);
-  const uint32_t bar0 = base + (uint32_t)S * stage_bytes;
+  const int b_slot = NB * b_slab;                // bytes of one ring slot
+  // shared memory: [SB weight-slab slots][barriers][tmem ptr][mask][index tile]
+  // tensor memory: [accumulator: c_out columns][S stages x A_COLS columns of the gathered A operand]
+  // The weight ring is as deep as ~56 KB allows and has its own barriers: the TMA bulk copies have ~1-2 us
+  // latency, so they must run many slabs ahead of the MMA (for C = 16 the whole layer fits: every weight byte
+  // is fetched once per CTA).
+  uint64_t* bars = (uint64_t*)(sm + (size_t)SB * b_slot);
+  const uint32_t bar0 = base + (uint32_t)SB * b_slot;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
-  const uint32_t tmem_full_bar = bar0 + 8u * (2 * S);
-  uint32_t* s_tmem = (uint32_t*)(bars + 2 * S + 1);
+  auto bfull_bar = [&](int j) { return bar0 + 8u * (2 * S + j); };
+  auto bempty_bar = [&](int j) { return bar0 + 8u * (2 * S + SB + j); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * S + 2 * SB);
+  uint32_t* s_tmem = (uint32_t*)(bars + 2 * S + 2 * SB + 1);
   uint32_t* s_mask = s_tmem + 1;
-  int32_t* s_idx = (int32_t*)(s_tmem + 4);
+  int32_t* s_idx = (int32_t*)(((uintptr_t)(s_tmem + 4) + 15) & ~(uintptr_t)15);  // 16-byte aligned
 
   // ---- tile -> rows ------------------------------------------------------------------------
   int64_t row0 = 0;
@@ -215,8 +225,12 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
   // ---- prologue ----------------------------------------------------------------------------
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 128 + 1);
+      mbar_init(full_bar(s), 128);
       mbar_init(empty_bar(s), 1);
+    }
+    for (int j = 0; j < SB; ++j) {
+      mbar_init(bfull_bar(j), 1);
+      mbar_init(bempty_bar(j), 1);
     }
     mbar_init(tmem_full_bar, 1);
     *s_mask = 0;
@@ -225,8 +239,29 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
   if (warp == 4) tmem_alloc(smem_u32(s_tmem), (uint32_t)a.tmem_cols);
   if (!PAIRS) {
     if (a.idx != nullptr) {
+      // stage the tile's slice of the neighbour table: 16-byte loads, all issued before the first store
+      // (the scalar load->store loop exposed one L2 latency per iteration: 18 x ~600 cycles per tile)
       const int32_t* p = a.idx + row0 * K;
-      for (int e = tid; e < rows * K; e += TC_THREADS) s_idx[e] = __ldg(p + e);
+      const int total = rows * K;
+      if ((((uintptr_t)p) & 15) == 0) {
+        const int n4 = total >> 2;
+        constexpr int U = 5;  // 128 * 27 / 4 = 864 int4 <= 192 * 5
+        int4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          int e4 = tid + u * TC_THREADS;
+          if (e4 < n4) v[u] = __ldg((const int4*)p + e4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          int e4 = tid + u * TC_THREADS;
+          if (e4 < n4) ((int4*)s_idx)[e4] = v[u];
+        }
+        for (int e4 = tid + U * TC_THREADS; e4 < n4; e4 += TC_THREADS) ((int4*)s_idx)[e4] = __ldg((const int4*)p + e4);
+        for (int e = (n4 << 2) + tid; e < total; e += TC_THREADS) s_idx[e] = __ldg(p + e);
+      } else {
+        for (int e = tid; e < total; e += TC_THREADS) s_idx[e] = __ldg(p + e);
+      }
     }
   } else {
     for (int e = tid; e < rows; e += TC_THREADS) {
@@ -272,12 +307,21 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
           if (PAIRS) g = s_idx[r];
           else g = (a.idx == nullptr) ? (int)(row0 + r) : s_idx[r * K + k];
         }
-        rowp = g >= 0 ? a.A + (int64_t)g * a.c_in : nullptr;
+        rowp = (g >= 0 && !(a.flags & 4)) ? a.A + (int64_t)g * a.c_in : nullptr;
       }
       if (rowp) {
-        const float4* p = (const float4*)(rowp + c * 16);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = __ldg(p + q);
+        // two 256-bit loads (LDG.E.256, sm_100): the L1TEX tag stage costs one wavefront per cache line and
+        // instruction, and this gather touches up to 32 different lines per warp instruction -- halving the
+        // instruction count halves the dominant cost (clock64 timeline in profiles/r01_conv_tc_timeline.txt)
+        const float* p = rowp + c * 16;
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(dst[0].x), "=f"(dst[0].y), "=f"(dst[0].z), "=f"(dst[0].w), "=f"(dst[1].x), "=f"(dst[1].y),
+                       "=f"(dst[1].z), "=f"(dst[1].w)
+                     : "l"(p));
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(dst[2].x), "=f"(dst[2].y), "=f"(dst[2].z), "=f"(dst[2].w), "=f"(dst[3].x), "=f"(dst[3].y),
+                       "=f"(dst[3].z), "=f"(dst[3].w)
+                     : "l"(p + 8));
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -285,10 +329,12 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
       ++c;
     };
     const uint32_t a_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a.a_col0;
+    int dbg_t = 0;
     int st_s = 0;        // stage of the next slab to store
     uint32_t st_ph = 0;  // its phase bit
     auto store_slab = [&](const float4 (&src)[4]) {
       mbar_wait(empty_bar(st_s), st_ph ^ 1u);
+      if ((a.flags & 16) && blockIdx.x == 0 && tid == 0 && dbg_t < 256) g_tc_debug[0][dbg_t] = clock64();
       tc_fence_after();
       uint32_t hi[16], lo[16];
 #pragma unroll
@@ -311,6 +357,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(full_bar(st_s));
+      if ((a.flags & 16) && blockIdx.x == 0 && tid == 0 && dbg_t < 256) g_tc_debug[1][dbg_t] = clock64();
+      ++dbg_t;
       if (++st_s == S) {
         st_s = 0;
         st_ph ^= 1u;
@@ -355,16 +403,19 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
     // =========================== MMA issuer (one thread) =====================================
     if (lane == 0 && T > 0) {
       const uint32_t idesc = make_idesc_tf32(a.c_out);
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, j = 0;
+      uint32_t ph = 0, bph = 0;
       for (int t = 0; t < T; ++t) {
+        mbar_wait(bfull_bar(j), bph);
         mbar_wait(full_bar(s), ph);
+        if ((a.flags & 16) && blockIdx.x == 0 && t < 256) g_tc_debug[2][t] = clock64();
         tc_fence_after();
-        const uint32_t b_hi = base + (uint32_t)s * stage_bytes;
+        const uint32_t b_hi = base + (uint32_t)j * b_slot;
         const uint64_t db_hi = make_desc_sw64(b_hi);
         const uint32_t ta_hi = tmem_base + (uint32_t)a.a_col0 + (uint32_t)(s * A_COLS);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {  // two K = 8 slices: +8 TMEM columns (A), +32 bytes = +2 encoded (B)
+          if (a.flags & 8) break;
           const uint32_t acc = (t > 0 || ks > 0) ? 1u : 0u;
           if (NSPLIT == 3) {
             const uint64_t db_lo = make_desc_sw64(b_hi + b_slab);
@@ -375,10 +426,16 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
             umma_tf32_ts(tmem_base, ta_hi + 8 * ks, db_hi + 2 * ks, idesc, acc);
           }
         }
-        umma_commit(empty_bar(s));  // frees the stage once the MMAs above have read it
+        umma_commit(empty_bar(s));    // frees the A stage once the MMAs above have read it
+        if ((a.flags & 16) && blockIdx.x == 0 && t < 256) g_tc_debug[3][t] = clock64();
+        if (T > SB) umma_commit(bempty_bar(j));  // ... and the weight slot (only recycled when the layer does not fit)
         if (++s == S) {
           s = 0;
           ph ^= 1u;
+        }
+        if (++j == SB) {
+          j = 0;
+          bph ^= 1u;
         }
       }
       umma_commit(tmem_full_bar);
@@ -388,8 +445,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
     // =========================== weight loader (one thread, TMA engine) ======================
     if (lane == 0 && T > 0) {
       uint32_t km = kmask;
-      int k = -1, c = nc, s = 0;
-      uint32_t ph = 0;
+      int k = -1, c = nc, j = 0;
+      uint32_t bph = 0;
       for (int t = 0; t < T; ++t) {
         if (c == nc) {
           k = __ffs(km) - 1;
@@ -397,16 +454,16 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
           c = 0;
         }
         const int kw = a.k_reversed ? (K - 1 - k) : k;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t b_hi = base + (uint32_t)s * stage_bytes;
+        mbar_wait(bempty_bar(j), bph ^ 1u);
+        const uint32_t b_hi = base + (uint32_t)j * b_slot;
         const float* src = a.Bp + ((int64_t)kw * nc + c) * (int64_t)(a.c_out * 16);
-        mbar_arrive_expect_tx(full_bar(s), (uint32_t)(NB * b_slab));
-        bulk_g2s(b_hi, src, (uint32_t)b_slab, full_bar(s));
-        if (NSPLIT == 3) bulk_g2s(b_hi + b_slab, src + a.bp_half, (uint32_t)b_slab, full_bar(s));
+        mbar_arrive_expect_tx(bfull_bar(j), (uint32_t)b_slot);
+        bulk_g2s(b_hi, src, (uint32_t)b_slab, bfull_bar(j));
+        if (NSPLIT == 3) bulk_g2s(b_hi + b_slab, src + a.bp_half, (uint32_t)b_slab, bfull_bar(j));
         ++c;
-        if (++s == S) {
-          s = 0;
-          ph ^= 1u;
+        if (++j == SB) {
+          j = 0;
+          bph ^= 1u;
         }
       }
     }
@@ -428,18 +485,19 @@ size_t conv_tc_ws_bytes(int K, int c_in, int c_out) { return align_up((size_t)K 
 template <bool PAIRS, int NSPLIT>
 static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream) {
   auto bucket = [](int c) { int b = 32; while (b < c) b <<= 1; return b; };
-  const int stage_bytes = (NSPLIT == 3 ? 2 : 1) * a.c_out * 64;
+  const int b_slot = (NSPLIT == 3 ? 2 : 1) * a.c_out * 64;
   const int a_cols = NSPLIT == 3 ? 32 : 16;
-  // as many stages as the tensor-memory bucket of (accumulator + 2 stages) holds, at most 6, within ~64 KB smem
+  // A stages: as many as the tensor-memory bucket of (accumulator + 2 stages) holds, at most 6
   int stages = 6;
-  while (stages > 2 && (bucket(a.c_out + stages * a_cols) > bucket(a.c_out + 2 * a_cols) ||
-                        (size_t)stages * stage_bytes > 64 * 1024))
-    --stages;
+  while (stages > 2 && bucket(a.c_out + stages * a_cols) > bucket(a.c_out + 2 * a_cols)) --stages;
   a.stages = stages;
   a.a_col0 = a.c_out;
   a.tmem_cols = bucket(a.c_out + stages * a_cols);
-  const size_t fixed = 1024 /*align slack*/ + 8 * (2 * 8 + 1) + 16 + (size_t)(PAIRS ? 2 * TC_BM : TC_BM * a.K) * 4 + 64;
-  size_t smem = (size_t)stages * stage_bytes + fixed;
+  // weight ring: every slab of the layer if that fits in 56 KB, else as many slots as 56 KB holds (>= 2)
+  const int total_slabs = a.K * (a.c_in / 16);
+  a.sb = std::max(2, std::min(std::min(total_slabs, 64), (56 * 1024) / b_slot));
+  const size_t fixed = 1024 /*align slack*/ + 8 * (2 * 8 + 2 * 64 + 1) + 16 + (size_t)(PAIRS ? 2 * TC_BM : TC_BM * a.K) * 4 + 64;
+  size_t smem = (size_t)a.sb * b_slot + fixed;
   auto kern = conv_tc_kernel<PAIRS, NSPLIT>;
   static size_t configured = 0;
   if (smem > configured) {
@@ -475,7 +533,11 @@ int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* d
   a.c_in = c_in;
   a.c_out = c_out;
   a.k_reversed = krev;
-  a.stages = a.tmem_cols = a.a_col0 = 0;
+  a.stages = a.tmem_cols = a.a_col0 = a.sb = 0;
+  {
+    const char* e = getenv("B2S_TC_DEBUG");
+    a.flags = e ? atoi(e) : 0;
+  }
   if (!pairs) {
     int64_t gx = cdiv(n_out, TC_BM);
     return nsplit == 3 ? launch_tc<false, 3>(a, gx, stream) : launch_tc<false, 1>(a, gx, stream);
@@ -485,3 +547,7 @@ int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* d
 }
 
 }  // namespace b2s
+
+extern "C" int b2s_debug_tc_timeline(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, b2s::g_tc_debug, sizeof(long long) * 4 * 256) == cudaSuccess ? 0 : -3;
+}
