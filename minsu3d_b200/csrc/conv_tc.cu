@@ -496,6 +496,12 @@ static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream) {
   // weight ring: every slab of the layer if that fits in 56 KB, else as many slots as 56 KB holds (>= 2)
   const int total_slabs = a.K * (a.c_in / 16);
   a.sb = std::max(2, std::min(std::min(total_slabs, 64), (56 * 1024) / b_slot));
+  if (const char* e = getenv("B2S_TC_SB")) a.sb = std::max(2, std::min(a.sb, atoi(e)));
+  if (const char* e = getenv("B2S_TC_STAGES")) {
+    stages = std::max(2, std::min(stages, atoi(e)));
+    a.stages = stages;
+    a.tmem_cols = bucket(a.c_out + stages * a_cols);
+  }
   const size_t fixed = 1024 /*align slack*/ + 8 * (2 * 8 + 2 * 64 + 1) + 16 + (size_t)(PAIRS ? 2 * TC_BM : TC_BM * a.K) * 4 + 64;
   size_t smem = (size_t)a.sb * b_slot + fixed;
   auto kern = conv_tc_kernel<PAIRS, NSPLIT>;
