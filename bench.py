@@ -12,6 +12,8 @@ Prints ONE JSON line on rank 0.
 import argparse
 import json
 import os
+
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")  # no cudaFree/cudaMalloc stalls when batch sizes vary
 import subprocess
 import sys
 import threading

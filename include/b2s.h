@@ -56,6 +56,8 @@ const char* b2s_last_error_string(void);
  *   inverse     [n] int32: unique row of every input row
  *   out_coords  [n,4] int32 (first m valid): quantised coordinates of the unique rows
  *   d_count     int32[2] on device: {m, range_error_flag}
+ *   d_n         optional device int32: the real number of input rows (<= n, n then being an upper bound);
+ *               lets a chain of strided maps (a coordinate pyramid) be built without host round trips
  * After the call the table maps packed coordinate -> unique row.
  * ---------------------------------------------------------------------------------------------- */
 int64_t b2s_hash_capacity(int64_t n);
@@ -63,7 +65,7 @@ size_t b2s_coord_unique_ws_bytes(int64_t n);
 int b2s_coord_unique(const int32_t* coords, int64_t n, int32_t quant,
                      uint64_t* table_keys, int32_t* table_vals, int64_t cap,
                      int32_t* unique_idx, int32_t* inverse, int32_t* out_coords,
-                     int32_t* d_count, void* ws, size_t ws_bytes, b2s_stream_t stream);
+                     int32_t* d_count, const int32_t* d_n, void* ws, size_t ws_bytes, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * T2 -- kernel map (output-stationary neighbour table).
@@ -120,16 +122,18 @@ int b2s_conv_wgrad(const float* A, const float* G, const int32_t* src, const int
 size_t b2s_bn_ws_bytes(int64_t n, int32_t c);
 /* batch statistics: mean, biased variance (optional), rstd = 1/sqrt(var+eps) (optional); when
  * running_mean/var are given they are updated in place with `momentum` and the unbiased variance. */
+/* counter: one int32 on the device that is ZERO between launches (the last block to finish runs the
+ * second reduction stage and resets it); a dedicated buffer, not part of the shared workspace.          */
 int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum, float* running_mean,
-                 float* running_var, float* mean, float* var_biased, float* rstd, void* ws,
-                 size_t ws_bytes, b2s_stream_t stream);
+                 float* running_var, float* mean, float* var_biased, float* rstd, int32_t* counter,
+                 void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_bn_apply(const float* x, int64_t n, int32_t c, const float* mean, const float* rstd,
                  const float* gamma, const float* beta, int32_t relu, float* y, b2s_stream_t stream);
 /* backward of y = relu?(gamma*(x-mean)*rstd + beta) in training mode:
  * dgamma, dbeta [C]; dx [n,C].  y is the forward output (for the ReLU mask).                     */
 int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, int32_t c,
                     const float* mean, const float* rstd, const float* gamma, int32_t relu,
-                    int32_t training, float* dx, float* dgamma, float* dbeta,
+                    int32_t training, float* dx, float* dgamma, float* dbeta, int32_t* counter,
                     void* ws, size_t ws_bytes, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -168,7 +172,8 @@ int b2s_ballquery_fill(const float* xyz, const uint8_t* batch_idxs, const int32_
  *     point_num_avg; cls: 0 = dropped, 1 = kept fragment, 2 = primary; fragments (size < high)
  *     are also listed when want_fragments.
  *     Outputs: d_count = {nCluster, sumNPoint}, cluster_offsets [nCluster+1], seeds [nCluster].
- * b2s_cluster_order : cluster_idxs [sumNPoint,2] (cluster id, point) in BFS visit order.
+ * b2s_cluster_order : cluster_idxs [sumNPoint,2] (cluster id, point) in BFS visit order; n_active (length of
+ *     nbr_idx) picks the per-cluster-CTA variant (sparse, deep graphs) or the device-wide one (dense graphs).
  * ---------------------------------------------------------------------------------------------- */
 size_t b2s_cluster_ws_bytes(int64_t n);
 int b2s_cluster_label(const int32_t* nbr_idx, const int32_t* start_len, const int16_t* labels,
@@ -178,7 +183,7 @@ int b2s_cluster_select(const int32_t* comp, const int16_t* labels, int64_t n, in
                        int32_t* cluster_offsets, int32_t* seeds, int32_t* d_count,
                        void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_cluster_order(const int32_t* nbr_idx, const int32_t* start_len, const int16_t* labels,
-                      const int32_t* comp, int64_t n, const int32_t* cluster_offsets,
+                      const int32_t* comp, int64_t n, int64_t n_active, const int32_t* cluster_offsets,
                       const int32_t* seeds, int32_t n_cluster, int32_t* cluster_idxs,
                       void* ws, size_t ws_bytes, b2s_stream_t stream);
 /* HAIS: centres [nCluster,5] = (sum_x/size, sum_y/size, sum_z/size, cls, batch), sums taken

@@ -105,6 +105,21 @@ class _ConvUp(torch.autograd.Function):
         return gin, gk, None
 
 
+_IDENT = {}
+
+
+def _identity_pairs(n, device):
+    """(arange(n) i32, k_offsets [0, n]) for the dense 1x1 case, cached per size."""
+    key = (n, device.index)
+    v = _IDENT.get(key)
+    if v is None:
+        if len(_IDENT) > 64:
+            _IDENT.clear()
+        v = _IDENT[key] = (torch.arange(n, dtype=torch.int32, device=device),
+                           torch.tensor([0, n], dtype=torch.int32, device=device))
+    return v
+
+
 class _Conv1x1(torch.autograd.Function):
     """kernel_size 1, stride 1: dense [M,Cin] @ [Cin,Cout] through the same implicit-GEMM kernel."""
 
@@ -125,7 +140,9 @@ class _Conv1x1(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gin = ops.conv_table(gout, kernel, None, feats.size(0), 1, cout, cin, w_transposed=True)
         if ctx.needs_input_grad[1]:
-            gk = feats.t().mm(gout)  # plain library GEMM for the 1x1 weight gradient
+            n = feats.size(0)
+            ident, koff = _identity_pairs(n, feats.device)
+            gk = ops.conv_wgrad(feats, gout, ident, ident, koff, 1, cin, cout, n).view(cin, cout)
         return gin, gk
 
 

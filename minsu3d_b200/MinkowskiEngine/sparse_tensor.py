@@ -91,14 +91,29 @@ class CoordinateManager:
     def size(self, key):
         return self._maps[key].size
 
+    # a MinkUNet strides down several times: when the first stride-2 map of a large tensor is requested the
+    # whole coordinate pyramid is built speculatively on the device with a single host read of all row counts
+    # (each level is at most half the previous one, unused levels are cheap); small tensors build one level.
+    PYRAMID_MIN_ROWS = 20000
+    PYRAMID_LEVELS = 6
+
     def stride_key(self, in_key, stride=2):
         """Coordinate map of tensor stride in*stride: unique(floor(c / new) * new), first-occurrence order."""
         new_stride = in_key.stride * int(stride)
         out_key = CoordinateMapKey(new_stride)
         if out_key not in self._maps:
             src = self._maps[in_key]
-            table, _, _, out_coords = ops.coord_unique(src.coords, quant=new_stride)
-            self._maps[out_key] = _CoordMap(out_coords, table, new_stride)
+            levels = 1
+            if int(stride) == 2 and src.size >= self.PYRAMID_MIN_ROWS:
+                levels = self.PYRAMID_LEVELS
+            if levels > 1:
+                for s, table, oc in ops.coord_pyramid(src.coords, in_key.stride, levels):
+                    key = CoordinateMapKey(s)
+                    if key not in self._maps:
+                        self._maps[key] = _CoordMap(oc, table, s)
+            else:
+                table, _, _, out_coords = ops.coord_unique(src.coords, quant=new_stride)
+                self._maps[out_key] = _CoordMap(out_coords, table, new_stride)
         return out_key
 
     def existing_key(self, stride):

@@ -26,7 +26,7 @@ _SIGNATURES = {
     "b2s_last_error_string": (ctypes.c_char_p, []),
     "b2s_hash_capacity": (c_i64, [c_i64]),
     "b2s_coord_unique_ws_bytes": (c_size, [c_i64]),
-    "b2s_coord_unique": (c_i32, [_P, c_i64, c_i32, _P, _P, c_i64, _P, _P, _P, _P, _P, c_size, _P]),
+    "b2s_coord_unique": (c_i32, [_P, c_i64, c_i32, _P, _P, c_i64, _P, _P, _P, _P, _P, _P, c_size, _P]),
     "b2s_kernel_map": (c_i32, [_P, c_i64, c_i32, c_i32, _P, _P, c_i64, _P, _P]),
     "b2s_pairs_ws_bytes": (c_size, [c_i64, c_i32]),
     "b2s_pairs_from_nbr": (c_i32, [_P, c_i64, c_i32, c_i64, _P, _P, _P, _P, _P, c_size, _P]),
@@ -35,9 +35,9 @@ _SIGNATURES = {
     "b2s_conv_pairs": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, _P, c_size, _P]),
     "b2s_conv_wgrad": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i64, c_i32, _P]),
     "b2s_bn_ws_bytes": (c_size, [c_i64, c_i32]),
-    "b2s_bn_stats": (c_i32, [_P, c_i64, c_i32, c_f32, c_f32, _P, _P, _P, _P, _P, _P, c_size, _P]),
+    "b2s_bn_stats": (c_i32, [_P, c_i64, c_i32, c_f32, c_f32, _P, _P, _P, _P, _P, _P, _P, c_size, _P]),
     "b2s_bn_apply": (c_i32, [_P, c_i64, c_i32, _P, _P, _P, _P, c_i32, _P, _P]),
-    "b2s_bn_backward": (c_i32, [_P, _P, _P, c_i64, c_i32, _P, _P, _P, c_i32, c_i32, _P, _P, _P, _P, c_size, _P]),
+    "b2s_bn_backward": (c_i32, [_P, _P, _P, c_i64, c_i32, _P, _P, _P, c_i32, c_i32, _P, _P, _P, _P, _P, c_size, _P]),
     "b2s_gather_rows": (c_i32, [_P, _P, c_i64, c_i32, _P, _P]),
     "b2s_scatter_add_rows": (c_i32, [_P, _P, c_i64, c_i32, _P, _P]),
     "b2s_ballquery_ws_bytes": (c_size, [c_i64]),
@@ -46,7 +46,7 @@ _SIGNATURES = {
     "b2s_cluster_ws_bytes": (c_size, [c_i64]),
     "b2s_cluster_label": (c_i32, [_P, _P, _P, c_i64, _P, _P, c_size, _P]),
     "b2s_cluster_select": (c_i32, [_P, _P, c_i64, c_i32, c_i32, c_f32, _P, c_i32, _P, _P, _P, _P, c_size, _P]),
-    "b2s_cluster_order": (c_i32, [_P, _P, _P, _P, c_i64, _P, _P, c_i32, _P, _P, c_size, _P]),
+    "b2s_cluster_order": (c_i32, [_P, _P, _P, _P, c_i64, c_i64, _P, _P, c_i32, _P, _P, c_size, _P]),
     "b2s_cluster_centers": (c_i32, [_P, _P, c_i32, _P, _P, _P, _P, _P]),
     "b2s_ha_assign": (c_i32, [_P, c_i32, _P, _P, c_i32, _P, _P, _P]),
     "b2s_ha_concat_ws_bytes": (c_size, [c_i32, c_i32]),
@@ -94,9 +94,9 @@ class _Namespace:
 # used for the `gpu_launches` figure of bench.py
 KERNELS_PER_CALL = {
     "b2s_coord_unique": 6, "b2s_kernel_map": 1, "b2s_pairs_from_nbr": 4, "b2s_conv_table": 2, "b2s_conv_pairs": 2,
-    "b2s_conv_wgrad": 1, "b2s_bn_stats": 2, "b2s_bn_apply": 1, "b2s_bn_backward": 3, "b2s_gather_rows": 1,
+    "b2s_conv_wgrad": 1, "b2s_bn_stats": 1, "b2s_bn_apply": 1, "b2s_bn_backward": 2, "b2s_gather_rows": 1,
     "b2s_scatter_add_rows": 1, "b2s_ballquery_count": 16, "b2s_ballquery_fill": 1, "b2s_cluster_label": 4,
-    "b2s_cluster_select": 7, "b2s_cluster_order": 1, "b2s_cluster_centers": 1, "b2s_ha_assign": 1,
+    "b2s_cluster_select": 7, "b2s_cluster_order": 4, "b2s_cluster_centers": 1, "b2s_ha_assign": 1,
     "b2s_ha_concat": 4, "b2s_sec_mean": 1, "b2s_sec_min": 1, "b2s_sec_max": 1, "b2s_roipool_fp": 1,
     "b2s_roipool_bp": 1, "b2s_global_avg_pool_fp": 1, "b2s_global_avg_pool_bp": 1, "b2s_get_iou": 1,
     "b2s_get_mask_label": 1,

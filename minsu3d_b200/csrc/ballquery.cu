@@ -157,18 +157,25 @@ __global__ void __launch_bounds__(BQ_WARPS * 32)
   int32_t* hit = s_hit[warp];
   int written = 0;
   while (written < need) {
+    // adaptive window: the BQ_CAND candidate slots of a round are shared by the cells that still have entries
+    // (dense blobs of shifted coordinates sit in 1-8 cells: 54-432 entries per cell and round instead of 16)
+    const unsigned alive = __ballot_sync(0xffffffffu, cur < end);
+    if (alive == 0) break;
+    const int step = BQ_CAND / __popc(alive);
     // window bound: only cells that extend past their window constrain the threshold
-    int wend = min(cur + BQ_STEP, end);
+    int wend = min(cur + step, end);
     int hi = 0x7fffffff;
-    if (wend < end) hi = __float_as_int(__ldg(rec + wend - 1).w);
+    if (wend < end) hi = __float_as_int(__ldg(&rec[wend - 1].w));
     int T = hi;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) T = min(T, __shfl_xor_sync(0xffffffffu, T, o));
-    // entries of my window with index <= T (a prefix, lists are ascending)
-    int take = 0;
-    for (int i = cur; i < wend; ++i) {
-      if (__float_as_int(__ldg(rec + i).w) <= T) ++take; else break;
+    // entries of my window with index <= T: a prefix (lists are ascending) -> binary search
+    int lo_i = cur, hi_i = wend;
+    while (lo_i < hi_i) {
+      int mid = (lo_i + hi_i) >> 1;
+      if (__float_as_int(__ldg(&rec[mid].w)) <= T) lo_i = mid + 1; else hi_i = mid;
     }
+    int take = lo_i - cur;
     // exclusive prefix over lanes
     int off = take;
 #pragma unroll
@@ -178,7 +185,15 @@ __global__ void __launch_bounds__(BQ_WARPS * 32)
     }
     int total = __shfl_sync(0xffffffffu, off, 31);
     off -= take;
-    for (int e = 0; e < take; ++e) cand[off + e] = cur + e;
+    // candidate positions, written cooperatively cell by cell (a single dense cell may contribute the whole round)
+    unsigned todo = __ballot_sync(0xffffffffu, take > 0);
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int tj = __shfl_sync(0xffffffffu, take, j), oj = __shfl_sync(0xffffffffu, off, j),
+                cj = __shfl_sync(0xffffffffu, cur, j);
+      for (int e = lane; e < tj; e += 32) cand[oj + e] = cj + e;
+    }
     cur += take;
     __syncwarp();
     if (total == 0) break;  // nothing left anywhere (cannot happen while written < need)

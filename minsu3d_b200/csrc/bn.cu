@@ -18,11 +18,18 @@ constexpr int BN_SLAB = 512;  // rows per CTA
 //   mode 1: p = dy*mask(y),   q = dy*mask(y) * (x-mean)*rstd
 // Thread t owns the float4 column (t % c4) and the row phase (t / c4); four independent 16-byte
 // loads are in flight per thread and array, fp32 partials are flushed into double every 32 rows.
+struct BnFinish {
+  // mode 0 (statistics): mean / var / rstd (+ running stats); mode 1 (gradients): dgamma / dbeta
+  float eps, momentum;
+  float *running_mean, *running_var, *out_a, *out_b, *out_c;  // stats: mean, var, rstd ; grads: dbeta, dgamma, -
+  int32_t* counter;  // zero between launches: the last block to finish does the second stage and resets it
+};
+
 __global__ void __launch_bounds__(BN_THREADS)
     bn_colsum_kernel(const float* __restrict__ x, const float* __restrict__ y,
                      const float* __restrict__ dy, const float* __restrict__ mean,
                      const float* __restrict__ rstd, int64_t n, int c, int mode, int relu,
-                     double* __restrict__ partial) {
+                     double* __restrict__ partial, BnFinish fin) {
   extern __shared__ double s_acc[];  // [rpp][2][c]
   const int c4 = c >> 2;
   const int rpp = BN_THREADS / c4 > 0 ? BN_THREADS / c4 : 1;  // row phases per pass
@@ -96,63 +103,58 @@ __global__ void __launch_bounds__(BN_THREADS)
     partial[((int64_t)blockIdx.x * 2 + 0) * c + ch] = sp;
     partial[((int64_t)blockIdx.x * 2 + 1) * c + ch] = sq;
   }
-}
-
-// deterministic second stage: 32 channels x 8 block-groups per CTA, fixed summation order
-__device__ __forceinline__ void bn_reduce_partials(const double* __restrict__ partial, int nblk, int c,
-                                                   double& sp, double& sq, int& ch) {
-  __shared__ double s_p[8][33], s_q[8][33];
-  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  ch = blockIdx.x * 32 + lane;
-  double a = 0.0, b = 0.0;
-  if (ch < c)
-    for (int blk = grp; blk < nblk; blk += 8) {
-      a += partial[((int64_t)blk * 2 + 0) * c + ch];
-      b += partial[((int64_t)blk * 2 + 1) * c + ch];
-    }
-  s_p[grp][lane] = a;
-  s_q[grp][lane] = b;
+  // ---- second stage by the last block to finish (fixed summation order -> deterministic) ----
+  __shared__ int s_last;
+  __threadfence();
   __syncthreads();
-  sp = 0.0;
-  sq = 0.0;
-  for (int g = 0; g < 8; ++g) {
-    sp += s_p[g][lane];
-    sq += s_q[g][lane];
+  if (threadIdx.x == 0) s_last = (atomicAdd(fin.counter, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nblk = gridDim.x;
+  // thread (g, ch): g-th slice of the blocks for channel ch; slices combined through shared memory
+  const int groups = BN_THREADS / c > 0 ? BN_THREADS / c : 1;  // >= 1 row groups when c <= 256
+  for (int ch0 = 0; ch0 < c; ch0 += BN_THREADS) {
+    const int ch = ch0 + threadIdx.x % (c < BN_THREADS ? c : BN_THREADS);
+    const int g = threadIdx.x / (c < BN_THREADS ? c : BN_THREADS);
+    double a = 0.0, b = 0.0;
+    if (ch < c && g < groups)
+      for (int blk = g; blk < nblk; blk += groups) {
+        a += __ldcg(partial + ((int64_t)blk * 2 + 0) * c + ch);
+        b += __ldcg(partial + ((int64_t)blk * 2 + 1) * c + ch);
+      }
+    __syncthreads();
+    if (ch < c && g < groups) {
+      s_acc[(g * 2 + 0) * c + ch] = a;
+      s_acc[(g * 2 + 1) * c + ch] = b;
+    }
+    __syncthreads();
+    if (g == 0 && ch < c) {
+      double sp = 0.0, sq = 0.0;
+      for (int h = 0; h < groups; ++h) {
+        sp += s_acc[(h * 2 + 0) * c + ch];
+        sq += s_acc[(h * 2 + 1) * c + ch];
+      }
+      if (mode == 0) {
+        double m = sp / (double)n;
+        double v = sq / (double)n - m * m;
+        v = v > 0.0 ? v : 0.0;
+        fin.out_a[ch] = (float)m;
+        if (fin.out_b) fin.out_b[ch] = (float)v;
+        if (fin.out_c) fin.out_c[ch] = (float)(1.0 / sqrt(v + (double)fin.eps));
+        if (fin.running_mean) {
+          double unbiased = n > 1 ? v * ((double)n / (double)(n - 1)) : v;
+          double mo = (double)fin.momentum;
+          fin.running_mean[ch] = (float)((1.0 - mo) * (double)fin.running_mean[ch] + mo * m);
+          fin.running_var[ch] = (float)((1.0 - mo) * (double)fin.running_var[ch] + mo * unbiased);
+        }
+      } else {
+        fin.out_a[ch] = (float)sp;  // dbeta
+        fin.out_b[ch] = (float)sq;  // dgamma
+      }
+    }
   }
-}
-
-// mean / rstd (+ running statistics with momentum, unbiased variance like torch.nn.BatchNorm1d)
-__global__ void __launch_bounds__(BN_THREADS)
-    bn_finish_stats_kernel(const double* __restrict__ partial, int nblk, int64_t n, int c, float eps,
-                           float momentum, float* __restrict__ running_mean,
-                           float* __restrict__ running_var, float* __restrict__ mean,
-                           float* __restrict__ var, float* __restrict__ rstd) {
-  double sp, sq;
-  int ch;
-  bn_reduce_partials(partial, nblk, c, sp, sq, ch);
-  if (threadIdx.x >= 32 || ch >= c) return;
-  double m = sp / (double)n;
-  double v = sq / (double)n - m * m;
-  v = v > 0.0 ? v : 0.0;
-  mean[ch] = (float)m;
-  if (var) var[ch] = (float)v;
-  if (rstd) rstd[ch] = (float)(1.0 / sqrt(v + (double)eps));
-  if (running_mean) {
-    double unbiased = n > 1 ? v * ((double)n / (double)(n - 1)) : v;
-    running_mean[ch] = (float)((1.0 - (double)momentum) * (double)running_mean[ch] + (double)momentum * m);
-    running_var[ch] = (float)((1.0 - (double)momentum) * (double)running_var[ch] + (double)momentum * unbiased);
-  }
-}
-
-__global__ void __launch_bounds__(BN_THREADS)
-    bn_finish_grad_kernel(const double* __restrict__ partial, int nblk, int c,
-                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  double sp, sq;
-  int ch;
-  bn_reduce_partials(partial, nblk, c, sp, sq, ch);
-  if (threadIdx.x >= 32 || ch >= c) return;
-  dbeta[ch] = (float)sp;
-  dgamma[ch] = (float)sq;
+  if (threadIdx.x == 0) *fin.counter = 0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -226,13 +228,13 @@ static int bn_check(int64_t n, int32_t c) {
 
 static size_t bn_smem(int c) {
   int c4 = c / 4;
-  int rpp = BN_THREADS / c4 > 0 ? BN_THREADS / c4 : 1;
-  return (size_t)rpp * 2 * c * 8;
+  int rpp = BN_THREADS / c4 > 0 ? BN_THREADS / c4 : 1;  // first stage: row phases
+  return (size_t)rpp * 2 * c * 8;                        // (second stage needs <= BN_THREADS/c groups: smaller)
 }
 
 int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum, float* running_mean,
-                 float* running_var, float* mean, float* var_biased, float* rstd, void* ws, size_t ws_bytes,
-                 b2s_stream_t stream) {
+                 float* running_var, float* mean, float* var_biased, float* rstd, int32_t* counter, void* ws,
+                 size_t ws_bytes, b2s_stream_t stream) {
   int rc = bn_check(n, c);
   if (rc) return rc;
   if (n == 0) return B2S_OK;
@@ -242,9 +244,8 @@ int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum
     return B2S_E_WORKSPACE;
   }
   double* partial = (double*)ws;
-  bn_colsum_kernel<<<nblk, BN_THREADS, bn_smem(c), stream>>>(x, nullptr, nullptr, nullptr, nullptr, n, c, 0, 0, partial);
-  bn_finish_stats_kernel<<<(unsigned)cdiv(c, 32), BN_THREADS, 0, stream>>>(partial, nblk, n, c, eps, momentum, running_mean,
-                                                                           running_var, mean, var_biased, rstd);
+  BnFinish fin{eps, momentum, running_mean, running_var, mean, var_biased, rstd, counter};
+  bn_colsum_kernel<<<nblk, BN_THREADS, bn_smem(c), stream>>>(x, nullptr, nullptr, nullptr, nullptr, n, c, 0, 0, partial, fin);
   return check_launch("bn_stats");
 }
 
@@ -261,7 +262,7 @@ int b2s_bn_apply(const float* x, int64_t n, int32_t c, const float* mean, const 
 
 int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, int32_t c,
                     const float* mean, const float* rstd, const float* gamma, int32_t relu,
-                    int32_t training, float* dx, float* dgamma, float* dbeta, void* ws,
+                    int32_t training, float* dx, float* dgamma, float* dbeta, int32_t* counter, void* ws,
                     size_t ws_bytes, b2s_stream_t stream) {
   int rc = bn_check(n, c);
   if (rc) return rc;
@@ -276,8 +277,8 @@ int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, 
     return B2S_E_WORKSPACE;
   }
   double* partial = (double*)ws;
-  bn_colsum_kernel<<<nblk, BN_THREADS, bn_smem(c), stream>>>(x, y, dy, mean, rstd, n, c, 1, relu, partial);
-  bn_finish_grad_kernel<<<(unsigned)cdiv(c, 32), BN_THREADS, 0, stream>>>(partial, nblk, c, dgamma, dbeta);
+  BnFinish fin{0.f, 0.f, nullptr, nullptr, dbeta, dgamma, nullptr, counter};
+  bn_colsum_kernel<<<nblk, BN_THREADS, bn_smem(c), stream>>>(x, y, dy, mean, rstd, n, c, 1, relu, partial, fin);
   int64_t total4 = n * (c / 4);
   bn_dx_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, stream>>>(
       (const float4*)x, (const float4*)y, (const float4*)dy, total4, c / 4, 1.0f / (float)n, mean, rstd,

@@ -46,9 +46,14 @@ __global__ void __launch_bounds__(256) insert_kernel(const int4* __restrict__ co
                                                      uint64_t* __restrict__ keys,
                                                      int32_t* __restrict__ vals, uint64_t mask,
                                                      int32_t* __restrict__ slot_of_row,
-                                                     int32_t* __restrict__ d_count) {
+                                                     int32_t* __restrict__ d_count,
+                                                     const int32_t* __restrict__ d_n) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
+  if (d_n && row >= *d_n) {  // n is only an upper bound: the real row count lives on the device
+    slot_of_row[row] = -1;
+    return;
+  }
   int4 c = coords[row];  // (b, x, y, z)
   if (quant > 1) {
     c.y = floor_div(c.y, quant) * quant;
@@ -89,9 +94,13 @@ __global__ void __launch_bounds__(256)
                        const int32_t* __restrict__ vals, const int32_t* __restrict__ slot_of_row,
                        const int32_t* __restrict__ rank, int32_t* __restrict__ unique_idx,
                        int32_t* __restrict__ inverse, int4* __restrict__ out_coords,
-                       int32_t* __restrict__ d_count) {
+                       int32_t* __restrict__ d_count, const int32_t* __restrict__ d_n) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n) return;
+  if (d_n && row >= *d_n) {
+    if (row == n - 1) d_count[0] = rank[row];
+    return;
+  }
   int s = slot_of_row[row];
   int w = s >= 0 ? vals[s] : row;
   int r = rank[w];
@@ -227,7 +236,7 @@ size_t b2s_coord_unique_ws_bytes(int64_t n) {
 
 int b2s_coord_unique(const int32_t* coords, int64_t n, int32_t quant, uint64_t* table_keys,
                      int32_t* table_vals, int64_t cap, int32_t* unique_idx, int32_t* inverse,
-                     int32_t* out_coords, int32_t* d_count, void* ws, size_t ws_bytes,
+                     int32_t* out_coords, int32_t* d_count, const int32_t* d_n, void* ws, size_t ws_bytes,
                      b2s_stream_t stream) {
   if (n < 0 || quant < 1 || cap < 2 * n || (cap & (cap - 1)) != 0 || n > 0x7fffffff / 32) {
     set_error("coord_unique: invalid n/quant/capacity");
@@ -249,13 +258,13 @@ int b2s_coord_unique(const int32_t* coords, int64_t n, int32_t quant, uint64_t* 
   }
   int grid = (int)cdiv(n, 256);
   insert_kernel<<<grid, 256, 0, stream>>>((const int4*)coords, (int)n, quant, table_keys, table_vals,
-                                          (uint64_t)cap - 1, slot_of_row, d_count);
+                                          (uint64_t)cap - 1, slot_of_row, d_count, d_n);
   flag_kernel<<<grid, 256, 0, stream>>>((int)n, table_vals, slot_of_row, flag);
   int rc = exclusive_scan_i32(flag, rank, n, sws, sbytes, stream);
   if (rc) return rc;
   emit_unique_kernel<<<grid, 256, 0, stream>>>((const int4*)coords, (int)n, quant, table_vals,
                                                slot_of_row, rank, unique_idx, inverse,
-                                               (int4*)out_coords, d_count);
+                                               (int4*)out_coords, d_count, d_n);
   remap_vals_kernel<<<grid, 256, 0, stream>>>((int)n, table_vals, slot_of_row, flag, rank);
   return check_launch("coord_unique");
 }

@@ -50,24 +50,26 @@ __global__ void __launch_bounds__(SEG_THREADS)
   }
 }
 
-// max / min with first-index-wins argmax: block per segment, warp w takes rows w, w+4, ...
-// op: 0 = max, 1 = min
+// max / min with first-index-wins argmax: block per segment.  Thread t owns channel (t % Cw) and row phase
+// (t / Cw) with Cw = min(C, 128): for the 3-channel coordinate reductions (sec_min / sec_max) 42 row phases work
+// in parallel instead of 3 active threads per block in the reference (sec_mean.cu:38-85).  op: 0 = max, 1 = min
 __global__ void __launch_bounds__(SEG_THREADS)
     seg_minmax_kernel(const float* __restrict__ inp, const int32_t* __restrict__ offsets,
                       float* __restrict__ out, int32_t* __restrict__ argidx, int n_seg, int c, int op) {
   extern __shared__ unsigned char s_raw[];
-  float* s_val = (float*)s_raw;                       // [4][c]
-  int32_t* s_idx = (int32_t*)(s_val + 4 * c);         // [4][c]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cw = c < SEG_THREADS ? c : SEG_THREADS;
+  const int phases = SEG_THREADS / cw;                 // >= 1
+  float* s_val = (float*)s_raw;                        // [phases][c]
+  int32_t* s_idx = (int32_t*)(s_val + phases * c);     // [phases][c]
+  const int ch0 = threadIdx.x % cw, ph = threadIdx.x / cw;
   const float init = (op == 0) ? -INFINITY : INFINITY;  // (float)(-1e50), sec_mean.cu:44,70
   for (int seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
-    int b = offsets[seg], e = offsets[seg + 1];
-    for (int ch0 = 0; ch0 < c; ch0 += 32) {
-      int ch = ch0 + lane;
-      float best = init;
-      int bi = -1;
-      if (ch < c) {
-        for (int r = b + warp; r < e; r += 4) {
+    const int b = offsets[seg], e = offsets[seg + 1];
+    if (ph < phases) {
+      for (int ch = ch0; ch < c; ch += cw) {
+        float best = init;
+        int bi = -1;
+        for (int r = b + ph; r < e; r += phases) {
           float v = __ldg(inp + (int64_t)r * c + ch);
           bool better = (op == 0) ? (v > best) : (v < best);
           if (better) {
@@ -75,20 +77,20 @@ __global__ void __launch_bounds__(SEG_THREADS)
             bi = r;
           }
         }
-        s_val[warp * c + ch] = best;
-        s_idx[warp * c + ch] = bi;
+        s_val[ph * c + ch] = best;
+        s_idx[ph * c + ch] = bi;
       }
     }
     __syncthreads();
     for (int ch = threadIdx.x; ch < c; ch += SEG_THREADS) {
       float best = init;
       int bi = -1;
-      for (int w = 0; w < 4; ++w) {
+      for (int w = 0; w < phases; ++w) {
         float v = s_val[w * c + ch];
         int i = s_idx[w * c + ch];
         if (i < 0) continue;
         bool better = (op == 0) ? (v > best) : (v < best);
-        if (better || (v == best && i < bi)) {
+        if (bi < 0 || better || (v == best && i < bi)) {
           best = v;
           bi = i;
         }
@@ -278,7 +280,8 @@ static int minmax(const float* inp, const int32_t* offsets, float* out, int32_t*
     return B2S_E_INVALID;
   }
   if (n_seg == 0) return B2S_OK;
-  size_t smem = (size_t)8 * c * 4;
+  const int cw = c < SEG_THREADS ? c : SEG_THREADS;
+  size_t smem = (size_t)2 * (SEG_THREADS / cw) * c * 4;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(seg_minmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   seg_minmax_kernel<<<seg_grid(n_seg), SEG_THREADS, smem, stream>>>(inp, offsets, out, arg, n_seg, c, op);

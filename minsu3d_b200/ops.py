@@ -30,10 +30,11 @@ class HashTable:
         self.vals = torch.empty(self.cap, dtype=I32, device=device)
 
 
-def coord_unique(coords, quant=1):
-    """First-occurrence unique of int32 [n,4] coordinates (optionally floor-quantised).
+def coord_unique_async(coords, quant=1, d_n=None):
+    """Enqueue insert + unique without reading the count back.
 
-    Returns (table, unique_idx[m] i32, inverse[n] i32, out_coords[m,4] i32).  One host read of m.
+    coords may be an upper-bound-sized buffer whose real row count is the device int32 d_n[0].
+    Returns (table, unique_idx_buf, inverse_buf, out_coords_buf, d_count) -- all sized by the upper bound.
     """
     require_cuda(coords)
     require(coords.dtype == I32 and coords.dim() == 2 and coords.size(1) == 4 and coords.is_contiguous(),
@@ -45,15 +46,42 @@ def coord_unique(coords, quant=1):
     inverse = _dev_i32(n, dev)
     out_coords = torch.empty((n, 4), dtype=I32, device=dev)
     d_count = _dev_i32(2, dev)
-    nbytes = lib().b2s_coord_unique_ws_bytes(n)
-    ws = workspace(nbytes, dev)
+    ws = workspace(lib().b2s_coord_unique_ws_bytes(n), dev)
     check(lib().b2s_coord_unique(ptr(coords), n, int(quant), ptr(table.keys), ptr(table.vals), table.cap,
-                                 ptr(unique_idx), ptr(inverse), ptr(out_coords), ptr(d_count), ptr(ws),
+                                 ptr(unique_idx), ptr(inverse), ptr(out_coords), ptr(d_count), ptr(d_n), ptr(ws),
                                  ws.numel(), stream()), "coord_unique")
+    return table, unique_idx, inverse, out_coords, d_count
+
+
+def coord_unique(coords, quant=1):
+    """First-occurrence unique of int32 [n,4] coordinates (optionally floor-quantised).
+
+    Returns (table, unique_idx[m] i32, inverse[n] i32, out_coords[m,4] i32).  One host read of m.
+    """
+    table, unique_idx, inverse, out_coords, d_count = coord_unique_async(coords, quant)
     m, bad = d_count.tolist()
     if bad:
         raise ValueError("coordinate outside the packable range (batch < 2^19, |xyz| < 2^14)")
     return table, unique_idx[:m], inverse, out_coords[:m]
+
+
+def coord_pyramid(coords, base_stride, levels):
+    """Strided maps base*2, base*4, ... built back to back on the device; ONE host read for all counts.
+
+    Returns a list of (stride, table, out_coords[m_l, 4]).
+    """
+    out, d_counts = [], []
+    cur, d_n, stride = coords, None, base_stride
+    for _ in range(levels):
+        stride *= 2
+        table, _, _, oc, d_count = coord_unique_async(cur, stride, d_n)
+        out.append((stride, table, oc))
+        d_counts.append(d_count)
+        cur, d_n = oc, d_count
+    counts = torch.stack(d_counts).tolist()
+    if any(bad for _, bad in counts):
+        raise ValueError("coordinate outside the packable range (batch < 2^19, |xyz| < 2^14)")
+    return [(s, t, oc[:m]) for (s, t, oc), (m, _) in zip(out, counts)]
 
 
 def kernel_map(out_coords, table, ksize, dil):
@@ -150,6 +178,18 @@ def conv_wgrad(A, G, src, dst, k_offsets, K, c_a, c_g, max_pairs, algo=None):
 # ------------------------------------------------------------------------------------------
 # T5 batch norm
 # ------------------------------------------------------------------------------------------
+_BN_COUNTERS = {}
+
+
+def _bn_counter(device):
+    """Per-(device, stream) int32 that is zero between launches (last-block-done second stage)."""
+    key = (device.index, stream())
+    t = _BN_COUNTERS.get(key)
+    if t is None:
+        t = _BN_COUNTERS[key] = torch.zeros(1, dtype=I32, device=device)
+    return t
+
+
 def bn_stats(x, eps=1e-5, momentum=0.0, running_mean=None, running_var=None):
     """Batch statistics in one call: returns (mean, rstd); updates the running statistics in place."""
     _f32c(x, "x")
@@ -158,7 +198,8 @@ def bn_stats(x, eps=1e-5, momentum=0.0, running_mean=None, running_var=None):
     rstd = torch.empty(c, dtype=torch.float32, device=x.device)
     ws = workspace(lib().b2s_bn_ws_bytes(n, c), x.device)
     check(lib().b2s_bn_stats(ptr(x), n, c, float(eps), float(momentum), ptr(running_mean), ptr(running_var),
-                             ptr(mean), None, ptr(rstd), ptr(ws), ws.numel(), stream()), "bn_stats")
+                             ptr(mean), None, ptr(rstd), ptr(_bn_counter(x.device)), ptr(ws), ws.numel(), stream()),
+          "bn_stats")
     return mean, rstd
 
 
@@ -180,7 +221,8 @@ def bn_backward(x, y, dy, mean, rstd, gamma, relu, training):
     dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
     ws = workspace(lib().b2s_bn_ws_bytes(n, c), x.device)
     check(lib().b2s_bn_backward(ptr(x), ptr(y), ptr(dy), n, c, ptr(mean), ptr(rstd), ptr(gamma), int(relu),
-                                int(training), ptr(dx), ptr(dgamma), ptr(dbeta), ptr(ws), ws.numel(), stream()),
+                                int(training), ptr(dx), ptr(dgamma), ptr(dbeta), ptr(_bn_counter(x.device)), ptr(ws),
+                                ws.numel(), stream()),
           "bn_backward")
     return dx, dgamma, dbeta
 
@@ -274,7 +316,8 @@ def cluster_extract(nbr_idx, start_len, labels, comp, mode, thr_i=0, thr_f=0.0, 
     cluster_idxs = torch.empty((total, 2), dtype=I32, device=dev)
     offsets = offsets[:n_cluster + 1]
     if n_cluster > 0:
-        check(lib().b2s_cluster_order(ptr(nbr_idx), ptr(start_len), ptr(labels), ptr(comp), n, ptr(offsets),
+        check(lib().b2s_cluster_order(ptr(nbr_idx), ptr(start_len), ptr(labels), ptr(comp), n, nbr_idx.numel(),
+                                      ptr(offsets),
                                       ptr(seeds), n_cluster, ptr(cluster_idxs), ptr(ws), ws.numel(), stream()),
               "cluster_order")
     return cluster_idxs, offsets

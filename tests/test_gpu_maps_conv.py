@@ -98,6 +98,23 @@ def test_strided_kernel_map_bit_exact():
     assert np.array_equal(inv[nbr[o, k]], o)
 
 
+def test_coordinate_pyramid_single_sync_matches_level_by_level_oracle():
+    """ops.coord_pyramid builds every strided map on the device (upper-bound buffers + device-side counts)."""
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(17)
+    c = surface_voxels(rng, 90_000, batch=3)
+    levels = ops.coord_pyramid(_dev(c), 1, 6)
+    cur = c
+    for (stride, table, oc), want_stride in zip(levels, (2, 4, 8, 16, 32, 64)):
+        assert stride == want_stride
+        _, _, want = oracle.coord_unique(cur, stride)
+        assert np.array_equal(oc.cpu().numpy(), want)
+        # the table answers lookups for the level's own coordinates: 1x1x1 kernel map = identity
+        nbr = ops.kernel_map(oc, table, 1, stride)
+        assert np.array_equal(nbr.cpu().numpy()[:, 0], np.arange(want.shape[0]))
+        cur = want
+
+
 CONV_SHAPES = [(6, 16), (16, 16), (32, 16), (32, 32), (48, 48), (64, 32), (64, 64), (96, 112), (224, 224), (20, 24)]
 
 
