@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
   // ---- prologue ----------------------------------------------------------------------------
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 128);
+      mbar_init(full_bar(s), 4);  // one arrival per producer warp
       mbar_init(empty_bar(s), 1);
     }
     for (int j = 0; j < SB; ++j) {
@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
       if (NSPLIT == 3) tmem_st16(col + 16, lo);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(full_bar(st_s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(st_s));  // 4 arrivals per slab instead of 128 serialised ones
       if ((a.flags & 16) && blockIdx.x == 0 && tid == 0 && dbg_t < 256) g_tc_debug[1][dbg_t] = clock64();
       ++dbg_t;
       if (++st_s == S) {
