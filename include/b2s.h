@@ -75,7 +75,7 @@ int b2s_coord_unique(const int32_t* coords, int64_t n, int32_t quant,
  * ---------------------------------------------------------------------------------------------- */
 int b2s_kernel_map(const int32_t* out_coords, int64_t n_out, int32_t ksize, int32_t dil,
                    const uint64_t* table_keys, const int32_t* table_vals, int64_t cap,
-                   int32_t* nbr, b2s_stream_t stream);
+                   int32_t* nbr, uint32_t* tile_mask, b2s_stream_t stream);
 
 /* Canonical per-offset pair lists (sorted by kidx, then by output row) from a neighbour table.
  *   pair_in/pair_out [>= number of pairs] int32, k_offsets [K+1] int32 (CSR over kidx),
@@ -93,6 +93,8 @@ int b2s_pairs_from_nbr(const int32_t* nbr, int64_t n_out, int32_t K, int64_t pai
  *     Wk = W[kk] (c_in x c_out, row-major) or its transpose when w_transposed (then W is
  *     [K, c_out, c_in] and the contraction runs over W's last axis), kk = k or K-1-k (k_reversed).
  *     nbr == NULL means K == 1 and the identity map (1x1 convolution = dense matmul).
+ *     tile_mask (may be NULL): the per-128-row active-offset masks b2s_kernel_map wrote for this nbr
+ *     (K <= 32); the tcgen05 path then skips empty offsets without scanning the table tile.
  *     forward: (A=in, W) ; data gradient of a stride-1 conv: (A=grad_out, w_transposed, k_reversed).
  * b2s_conv_pairs: for every pair p in [k_offsets[k], k_offsets[k+1]):
  *     out[dst[p], :] = A[src[p], :] @ Wk   (each dst row appears once; plain store)
@@ -102,8 +104,8 @@ int b2s_pairs_from_nbr(const int32_t* nbr, int64_t n_out, int32_t K, int64_t pai
  *       1 = fp32 FMA (SIMT), 2 = tcgen05 3xTF32 (fp32-class accuracy), 3 = tcgen05 plain TF32.
  * ---------------------------------------------------------------------------------------------- */
 size_t b2s_conv_ws_bytes(int32_t K, int32_t c_in, int32_t c_out); /* scratch for the packed weights */
-int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, float* out,
-                   int64_t n_out, int32_t K, int32_t c_in, int32_t c_out,
+int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, const uint32_t* tile_mask,
+                   float* out, int64_t n_out, int32_t K, int32_t c_in, int32_t c_out,
                    int32_t w_transposed, int32_t k_reversed, int32_t algo,
                    void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_conv_pairs(const float* A, const float* W, const int32_t* src, const int32_t* dst,
@@ -234,12 +236,7 @@ int b2s_get_mask_label(const int32_t* proposals_idx, const int32_t* proposals_of
                        int32_t ignored_label, float iou_thr, uint8_t* mask_label,
                        uint8_t* mask_label_mask, b2s_stream_t stream);
 
-/* ------------------------------------------------------------------------------------------------
- * Diagnostics: SM-clock timeline of CTA 0 of the last tcgen05 convolution launched with the
- * environment variable B2S_TC_DEBUG=16 (producer wait/arrive, MMA wake/commit per slab).
- * host_out: int64 [4][256] in HOST memory.  Used only by profiling scripts.
- * ---------------------------------------------------------------------------------------------- */
-int b2s_debug_tc_timeline(long long* host_out);
+
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ class _ConvSame(torch.autograd.Function):
     def forward(ctx, feats, kernel, kmap):
         feats = feats.contiguous()
         K, cin, cout = kernel.shape
-        out = ops.conv_table(feats, kernel, kmap.nbr, kmap.n_out, K, cin, cout)
+        out = ops.conv_table(feats, kernel, kmap.nbr, kmap.n_out, K, cin, cout, tile_mask=kmap.tile_mask)
         ctx.save_for_backward(feats, kernel)
         ctx.kmap = kmap
         return out
@@ -39,7 +39,8 @@ class _ConvSame(torch.autograd.Function):
         gin = gk = None
         if ctx.needs_input_grad[0]:
             # nbr[i, K-1-k] = o  <=>  nbr[o, k] = i: reuse the table with reversed, transposed weights
-            gin = ops.conv_table(gout, kernel, kmap.nbr, kmap.n_in, K, cout, cin, w_transposed=True, k_reversed=True)
+            gin = ops.conv_table(gout, kernel, kmap.nbr, kmap.n_in, K, cout, cin, w_transposed=True, k_reversed=True,
+                                 tile_mask=kmap.tile_mask)
         if ctx.needs_input_grad[1]:
             pin, pout, koff, maxp = kmap.pairs()
             gk = ops.conv_wgrad(feats, gout, pin, pout, koff, K, cin, cout, maxp)
@@ -53,7 +54,7 @@ class _ConvDown(torch.autograd.Function):
     def forward(ctx, feats, kernel, kmap):
         feats = feats.contiguous()
         K, cin, cout = kernel.shape
-        out = ops.conv_table(feats, kernel, kmap.nbr, kmap.n_out, K, cin, cout)
+        out = ops.conv_table(feats, kernel, kmap.nbr, kmap.n_out, K, cin, cout, tile_mask=kmap.tile_mask)
         ctx.save_for_backward(feats, kernel)
         ctx.kmap = kmap
         return out
@@ -98,7 +99,8 @@ class _ConvUp(torch.autograd.Function):
         gout = gout.contiguous()
         gin = gk = None
         if ctx.needs_input_grad[0]:
-            gin = ops.conv_table(gout, kernel, kmap.nbr, kmap.n_out, K, cout, cin, w_transposed=True)
+            gin = ops.conv_table(gout, kernel, kmap.nbr, kmap.n_out, K, cout, cin, w_transposed=True,
+                                 tile_mask=kmap.tile_mask)
         if ctx.needs_input_grad[1]:
             pin, pout, koff, maxp = kmap.pairs()
             gk = ops.conv_wgrad(feats, gout, pout, pin, koff, K, cin, cout, maxp)

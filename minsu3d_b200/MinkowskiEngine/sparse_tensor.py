@@ -52,8 +52,9 @@ class _CoordMap:
 class KernelMap:
     """Output-stationary neighbour table + lazily built canonical pair lists."""
 
-    def __init__(self, nbr, n_in, n_out, exact_pairs=None):
+    def __init__(self, nbr, n_in, n_out, exact_pairs=None, tile_mask=None):
         self.nbr = nbr
+        self.tile_mask = tile_mask  # per-128-row active-offset masks (ops.kernel_map), None = let the kernel scan
         self.n_in = n_in
         self.n_out = n_out
         self.K = nbr.size(1)
@@ -129,9 +130,9 @@ class CoordinateManager:
         km = self._kmaps.get(ck)
         if km is None:
             src, dst = self._maps[in_key], self._maps[out_key]
-            nbr = ops.kernel_map(dst.coords, src.table, int(kernel_size), src.stride)
+            nbr, tile_mask = ops.kernel_map(dst.coords, src.table, int(kernel_size), src.stride, with_tile_mask=True)
             exact = src.size if (out_key.stride != in_key.stride) else None  # 2^3/s2: one parent per input row
-            km = KernelMap(nbr, src.size, dst.size, exact_pairs=exact)
+            km = KernelMap(nbr, src.size, dst.size, exact_pairs=exact, tile_mask=tile_mask)
             self._kmaps[ck] = km
         return km
 

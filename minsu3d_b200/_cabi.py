@@ -27,11 +27,11 @@ _SIGNATURES = {
     "b2s_hash_capacity": (c_i64, [c_i64]),
     "b2s_coord_unique_ws_bytes": (c_size, [c_i64]),
     "b2s_coord_unique": (c_i32, [_P, c_i64, c_i32, _P, _P, c_i64, _P, _P, _P, _P, _P, _P, c_size, _P]),
-    "b2s_kernel_map": (c_i32, [_P, c_i64, c_i32, c_i32, _P, _P, c_i64, _P, _P]),
+    "b2s_kernel_map": (c_i32, [_P, c_i64, c_i32, c_i32, _P, _P, c_i64, _P, _P, _P]),
     "b2s_pairs_ws_bytes": (c_size, [c_i64, c_i32]),
     "b2s_pairs_from_nbr": (c_i32, [_P, c_i64, c_i32, c_i64, _P, _P, _P, _P, _P, c_size, _P]),
     "b2s_conv_ws_bytes": (c_size, [c_i32, c_i32, c_i32]),
-    "b2s_conv_table": (c_i32, [_P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P, c_size, _P]),
+    "b2s_conv_table": (c_i32, [_P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P, c_size, _P]),
     "b2s_conv_pairs": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, _P, c_size, _P]),
     "b2s_conv_wgrad": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i64, c_i32, _P]),
     "b2s_bn_ws_bytes": (c_size, [c_i64, c_i32]),
@@ -60,7 +60,6 @@ _SIGNATURES = {
     "b2s_global_avg_pool_bp": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
     "b2s_get_iou": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, _P]),
     "b2s_get_mask_label": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_f32, _P, _P, _P]),
-    "b2s_debug_tc_timeline": (c_i32, [_P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -9,6 +9,7 @@ int conv_wgrad_simt(const float*, const float*, const int32_t*, const int32_t*, 
 bool conv_tc_supported(int K, int c_in, int c_out);
 size_t conv_tc_ws_bytes(int K, int c_in, int c_out);
 int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* dst, const int32_t* k_offsets,
+            const uint32_t* tile_mask,
             float* out, int64_t n_out, int64_t max_pairs, int K, int c_in, int c_out, int wT, int krev, int nsplit,
             bool pairs, void* ws, size_t ws_bytes, cudaStream_t stream);
 }  // namespace b2s
@@ -35,8 +36,8 @@ size_t b2s_conv_ws_bytes(int32_t K, int32_t c_in, int32_t c_out) {
   return conv_tc_supported(K, c_in, c_out) ? conv_tc_ws_bytes(K, c_in, c_out) : 256;
 }
 
-int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, float* out, int64_t n_out,
-                   int32_t K, int32_t c_in, int32_t c_out, int32_t w_transposed, int32_t k_reversed,
+int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, const uint32_t* tile_mask, float* out,
+                   int64_t n_out, int32_t K, int32_t c_in, int32_t c_out, int32_t w_transposed, int32_t k_reversed,
                    int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream) {
   if (n_out < 0 || K < 1 || K > 125 || c_in < 1 || c_out < 1 || (nbr == nullptr && K != 1)) {
     set_error("conv_table: invalid argument");
@@ -46,8 +47,8 @@ int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, float* ou
   algo = pick(algo, K, c_in, c_out, "conv_table", &nsplit);
   if (algo < 0) return B2S_E_INVALID;
   if (algo >= 2)
-    return conv_tc(A, W, nbr, nullptr, nullptr, out, n_out, 0, K, c_in, c_out, w_transposed, k_reversed, nsplit, false,
-                   ws, ws_bytes, stream);
+    return conv_tc(A, W, nbr, nullptr, nullptr, tile_mask, out, n_out, 0, K, c_in, c_out, w_transposed, k_reversed,
+                   nsplit, false, ws, ws_bytes, stream);
   return conv_table_simt(A, W, nbr, out, n_out, K, c_in, c_out, w_transposed, k_reversed, stream);
 }
 
@@ -63,8 +64,8 @@ int b2s_conv_pairs(const float* A, const float* W, const int32_t* src, const int
   algo = pick(algo, K, c_in, c_out, "conv_pairs", &nsplit);
   if (algo < 0) return B2S_E_INVALID;
   if (algo >= 2)
-    return conv_tc(A, W, src, dst, k_offsets, out, 0, max_pairs, K, c_in, c_out, w_transposed, 0, nsplit, true, ws,
-                   ws_bytes, stream);
+    return conv_tc(A, W, src, dst, k_offsets, nullptr, out, 0, max_pairs, K, c_in, c_out, w_transposed, 0, nsplit, true,
+                   ws, ws_bytes, stream);
   return conv_pairs_simt(A, W, src, dst, k_offsets, out, K, c_in, c_out, w_transposed, max_pairs, stream);
 }
 

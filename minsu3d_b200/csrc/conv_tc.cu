@@ -63,6 +63,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// one lane of a converged warp (ELECT): keeps the surrounding control flow warp-uniform, so descriptors and
+// barrier addresses stay in uniform registers (a lane == 0 branch makes ptxas wrap every tcgen05/UBLKCP
+// instruction in a R2UR waterfall loop: ~40 instructions and ~80 cycles per MMA, measured)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -151,8 +163,8 @@ __global__ void __launch_bounds__(256)
   Bp[total + off] = lo;
 }
 
-// timeline instrumentation for CTA 0 (flag 16 of B2S_TC_DEBUG): [role][slab] SM clock
-__device__ long long g_tc_debug[4][256];
+// what a missing neighbour reads (keeps the gather loop branch-free); 256 floats = widest supported row
+__device__ float g_zero_row[256];
 
 struct TcArgs {
   const float* A;
@@ -160,11 +172,11 @@ struct TcArgs {
   const int32_t* idx;    // TABLE: nbr [n_out, K] (or NULL = identity, K == 1); PAIRS: src
   const int32_t* dst;    // PAIRS: destination rows
   const int32_t* k_offsets;
+  const uint32_t* tile_mask;  // TABLE, optional: active-offset mask per tile (b2s_kernel_map)
   float* out;
   int64_t n_out;
   int64_t bp_half;       // floats in one image
   int K, c_in, c_out, k_reversed, stages, tmem_cols, a_col0;
-  int flags;  // ablation switches (env B2S_TC_DEBUG): 4 = no gathered loads, 8 = no MMA issue
   int sb;  // weight-slab ring depth (shared memory), decoupled from the A stages (tensor memory)
 };
 
@@ -194,7 +206,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
   const uint32_t tmem_full_bar = bar0 + 8u * (2 * S + 2 * SB);
   uint32_t* s_tmem = (uint32_t*)(bars + 2 * S + 2 * SB + 1);
   uint32_t* s_mask = s_tmem + 1;
-  int32_t* s_idx = (int32_t*)(((uintptr_t)(s_tmem + 4) + 15) & ~(uintptr_t)15);  // 16-byte aligned
+  // 16-byte aligned (base is 1024-aligned); plain pointer arithmetic on the shared array keeps the address space
+  int32_t* s_idx = (int32_t*)(sm + (((size_t)SB * b_slot + 8u * (2 * S + 2 * SB + 1) + 16u + 15u) & ~(size_t)15));
 
   // ---- tile -> rows ------------------------------------------------------------------------
   int64_t row0 = 0;
@@ -223,29 +236,28 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
   }
 
   // ---- prologue ----------------------------------------------------------------------------
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(full_bar(s), 4);  // one arrival per producer warp
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int j = 0; j < SB; ++j) {
-      mbar_init(bfull_bar(j), 1);
-      mbar_init(bempty_bar(j), 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    *s_mask = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  {
+    // one barrier per thread (a serial loop over ~60 barriers by one thread cost ~1.8k cycles per tile)
+    const int nbar = 2 * S + 2 * SB + 1;
+    if (tid < nbar) mbar_init(bar0 + 8u * tid, (tid < S) ? 4u : 1u);  // full[s]: one arrival per producer warp
+    if (tid == 0) *s_mask = 0;
+    if (tid < nbar) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc(smem_u32(s_tmem), (uint32_t)a.tmem_cols);
+  // Stage the tile's gather indices for all 128 rows (-1 = no row: the producers then read the zero row, so
+  // their loop has no row/tile-edge branches) and build the active-offset mask from the same registers
+  // (or take it from b2s_kernel_map's per-tile masks).
+  uint32_t pre_mask = 0;
   if (!PAIRS) {
     if (a.idx != nullptr) {
-      // stage the tile's slice of the neighbour table: 16-byte loads, all issued before the first store
-      // (the scalar load->store loop exposed one L2 latency per iteration: 18 x ~600 cycles per tile)
       const int32_t* p = a.idx + row0 * K;
       const int total = rows * K;
+      const bool scan = (a.tile_mask == nullptr);
+      if (!scan) pre_mask = __ldg(a.tile_mask + blockIdx.x);
+      uint32_t m = 0;
       if ((((uintptr_t)p) & 15) == 0) {
         const int n4 = total >> 2;
-        constexpr int U = 5;  // 128 * 27 / 4 = 864 int4 <= 192 * 5
+        constexpr int U = 5;  // 128 * 27 / 4 = 864 int4 <= 192 * 5; all loads issued before the first store
         int4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -255,100 +267,108 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           int e4 = tid + u * TC_THREADS;
-          if (e4 < n4) ((int4*)s_idx)[e4] = v[u];
+          if (e4 < n4) {
+            ((int4*)s_idx)[e4] = v[u];
+            if (scan) {
+              int k0 = (e4 * 4) % K;
+              const int vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                m |= (vv[i] >= 0) ? (1u << k0) : 0u;
+                k0 = (k0 + 1 == K) ? 0 : k0 + 1;
+              }
+            }
+          }
         }
-        for (int e4 = tid + U * TC_THREADS; e4 < n4; e4 += TC_THREADS) ((int4*)s_idx)[e4] = __ldg((const int4*)p + e4);
-        for (int e = (n4 << 2) + tid; e < total; e += TC_THREADS) s_idx[e] = __ldg(p + e);
+        for (int e4 = tid + U * TC_THREADS; e4 < n4; e4 += TC_THREADS) {  // K > 27 only
+          int4 w = __ldg((const int4*)p + e4);
+          ((int4*)s_idx)[e4] = w;
+          const int vv[4] = {w.x, w.y, w.z, w.w};
+          for (int i = 0; i < 4; ++i) m |= (vv[i] >= 0) ? (1u << ((e4 * 4 + i) % K)) : 0u;
+        }
+        for (int e = (n4 << 2) + tid; e < total; e += TC_THREADS) {
+          int g = __ldg(p + e);
+          s_idx[e] = g;
+          m |= (g >= 0) ? (1u << (e % K)) : 0u;
+        }
       } else {
-        for (int e = tid; e < total; e += TC_THREADS) s_idx[e] = __ldg(p + e);
+        for (int e = tid; e < total; e += TC_THREADS) {
+          int g = __ldg(p + e);
+          s_idx[e] = g;
+          m |= (g >= 0) ? (1u << (e % K)) : 0u;
+        }
       }
+      for (int e = total + tid; e < TC_BM * K; e += TC_THREADS) s_idx[e] = -1;  // rows past the end of the table
+      if (scan) {
+        m = __reduce_or_sync(0xffffffffu, m);
+        if (lane == 0 && m) atomicOr(s_mask, m);
+      }
+    } else {
+      if (tid < TC_BM) s_idx[tid] = (tid < rows) ? (int)(row0 + tid) : -1;  // identity map (1x1 conv), K == 1
     }
   } else {
-    for (int e = tid; e < rows; e += TC_THREADS) {
-      s_idx[e] = a.idx[p0 + e];
-      s_idx[TC_BM + e] = a.dst[p0 + e];
+    for (int e = tid; e < TC_BM; e += TC_THREADS) {
+      s_idx[e] = (e < rows) ? a.idx[p0 + e] : -1;
+      s_idx[TC_BM + e] = (e < rows) ? a.dst[p0 + e] : -1;
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // active-offset mask of the tile
-  if (!PAIRS && a.idx != nullptr && warp < 4) {
-    uint32_t m = 0;
-    if (tid < rows)
-      for (int k = 0; k < K; ++k) m |= (s_idx[tid * K + k] >= 0) ? (1u << k) : 0u;
-    m = __reduce_or_sync(0xffffffffu, m);
-    if (lane == 0 && m) atomicOr(s_mask, m);
-  }
-  __syncthreads();
   uint32_t kmask;
   if (PAIRS) kmask = 1u << k_single;
-  else kmask = (a.idx == nullptr) ? 1u : *s_mask;
+  else if (a.idx == nullptr) kmask = 1u;
+  else kmask = (a.tile_mask != nullptr) ? pre_mask : *s_mask;
   const uint32_t tmem_base = *s_tmem;
   const int nc = a.c_in >> 4;
   const int T = __popc(kmask) * nc;  // slabs of this tile
 
   if (warp < 4) {
     // =========================== gather producers (thread = tile row = TMEM lane) ============
-    // Three register slots rotate (slab t+2 is loaded while slab t is written to tensor memory): two
-    // slabs of gathered data (8 x 16 B per thread) are in flight.
+    // Three register slots rotate (slab t+2 is loaded while slab t is written to tensor memory): two slabs of
+    // gathered data (2 x 64 B per thread) are in flight.  The loop body is branch-free apart from the uniform
+    // trip-count tests: a warp issues in order, so every divergent branch / dependent latency in the per-slab
+    // chain directly lengthens the slab period.
     const int r = tid;
+    const float* __restrict__ Ag = a.A;
+    const int c_in = a.c_in;
+    const int32_t* my_idx = s_idx + (PAIRS ? r : r * K);
     uint32_t km = kmask;
-    int c = nc;  // iterator state of the NEXT slab to load
-    const float* rowp = nullptr;
-    float4 ra[4], rb[4], rc[4];
-    auto load_next = [&](float4 (&dst)[4]) {
-      if (c == nc) {
-        const int k = __ffs(km) - 1;
-        km &= km - 1;
-        c = 0;
-        int g = -1;
-        if (r < rows) {
-          if (PAIRS) g = s_idx[r];
-          else g = (a.idx == nullptr) ? (int)(row0 + r) : s_idx[r * K + k];
-        }
-        rowp = (g >= 0 && !(a.flags & 4)) ? a.A + (int64_t)g * a.c_in : nullptr;
-      }
-      if (rowp) {
-        // two 256-bit loads (LDG.E.256, sm_100): the L1TEX tag stage costs one wavefront per cache line and
-        // instruction, and this gather touches up to 32 different lines per warp instruction -- halving the
-        // instruction count halves the dominant cost (clock64 timeline in profiles/r01_conv_tc_timeline.txt)
-        const float* p = rowp + c * 16;
-        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=f"(dst[0].x), "=f"(dst[0].y), "=f"(dst[0].z), "=f"(dst[0].w), "=f"(dst[1].x), "=f"(dst[1].y),
-                       "=f"(dst[1].z), "=f"(dst[1].w)
-                     : "l"(p));
-        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=f"(dst[2].x), "=f"(dst[2].y), "=f"(dst[2].z), "=f"(dst[2].w), "=f"(dst[3].x), "=f"(dst[3].y),
-                       "=f"(dst[3].z), "=f"(dst[3].w)
-                     : "l"(p + 8));
-      } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      ++c;
+    int lk = 0, lc = 0;  // kernel offset / channel chunk of the NEXT slab to load
+    float ra[16], rb[16], rc[16];
+    auto load_next = [&](float (&dst)[16]) {
+      const bool adv = (lc == 0);
+      const int kn = __ffs(km) - 1;
+      lk = adv ? kn : lk;
+      km = adv ? (km & (km - 1)) : km;
+      const int g = my_idx[PAIRS ? 0 : lk];
+      const float* p = (g >= 0) ? Ag + ((int64_t)g * c_in + lc * 16) : g_zero_row;
+      // two 256-bit loads (LDG.E.256, sm_100) per slab and thread
+      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(dst[0]), "=f"(dst[1]), "=f"(dst[2]), "=f"(dst[3]), "=f"(dst[4]), "=f"(dst[5]), "=f"(dst[6]),
+                     "=f"(dst[7])
+                   : "l"(p));
+      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(dst[8]), "=f"(dst[9]), "=f"(dst[10]), "=f"(dst[11]), "=f"(dst[12]), "=f"(dst[13]),
+                     "=f"(dst[14]), "=f"(dst[15])
+                   : "l"(p + 8));
+      lc = (lc + 1 == nc) ? 0 : lc + 1;
     };
     const uint32_t a_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a.a_col0;
-    int dbg_t = 0;
     int st_s = 0;        // stage of the next slab to store
     uint32_t st_ph = 0;  // its phase bit
-    auto store_slab = [&](const float4 (&src)[4]) {
+    auto store_slab = [&](const float (&src)[16]) {
       mbar_wait(empty_bar(st_s), st_ph ^ 1u);
-      if ((a.flags & 16) && blockIdx.x == 0 && tid == 0 && dbg_t < 256) g_tc_debug[0][dbg_t] = clock64();
       tc_fence_after();
       uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float v[4] = {src[q].x, src[q].y, src[q].z, src[q].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (NSPLIT == 3) {
-            uint32_t h = __float_as_uint(v[j]) & 0xFFFFE000u;
-            hi[4 * q + j] = h;
-            lo[4 * q + j] = __float_as_uint(v[j] - __uint_as_float(h));
-          } else {
-            hi[4 * q + j] = __float_as_uint(v[j]);
-          }
+      for (int j = 0; j < 16; ++j) {
+        if (NSPLIT == 3) {
+          const uint32_t h = __float_as_uint(src[j]) & 0xFFFFE000u;
+          hi[j] = h;
+          lo[j] = __float_as_uint(src[j] - __uint_as_float(h));
+        } else {
+          hi[j] = __float_as_uint(src[j]);
         }
       }
       const uint32_t col = a_lane + (uint32_t)(st_s * A_COLS);
@@ -358,12 +378,9 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(st_s));  // 4 arrivals per slab instead of 128 serialised ones
-      if ((a.flags & 16) && blockIdx.x == 0 && tid == 0 && dbg_t < 256) g_tc_debug[1][dbg_t] = clock64();
-      ++dbg_t;
-      if (++st_s == S) {
-        st_s = 0;
-        st_ph ^= 1u;
-      }
+      const bool wrap = (st_s + 1 == S);
+      st_s = wrap ? 0 : st_s + 1;
+      st_ph ^= wrap ? 1u : 0u;
     };
     if (T > 0) load_next(ra);
     if (T > 1) load_next(rb);
@@ -401,35 +418,38 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
     }
     tc_fence_before();
   } else if (warp == 4) {
-    // =========================== MMA issuer (one thread) =====================================
-    if (lane == 0 && T > 0) {
+    // =========================== MMA issuer ===================================================
+    // the whole warp runs the loop (uniform control flow); one elected lane issues
+    if (T > 0) {
       const uint32_t idesc = make_idesc_tf32(a.c_out);
+      const bool recycle_b = T > SB;
       int s = 0, j = 0;
       uint32_t ph = 0, bph = 0;
       for (int t = 0; t < T; ++t) {
         mbar_wait(bfull_bar(j), bph);
         mbar_wait(full_bar(s), ph);
-        if ((a.flags & 16) && blockIdx.x == 0 && t < 256) g_tc_debug[2][t] = clock64();
         tc_fence_after();
-        const uint32_t b_hi = base + (uint32_t)j * b_slot;
-        const uint64_t db_hi = make_desc_sw64(b_hi);
-        const uint32_t ta_hi = tmem_base + (uint32_t)a.a_col0 + (uint32_t)(s * A_COLS);
+        if (elect_one()) {
+          const uint32_t b_hi = base + (uint32_t)j * b_slot;
+          const uint64_t db_hi = make_desc_sw64(b_hi);
+          const uint32_t ta_hi = tmem_base + (uint32_t)a.a_col0 + (uint32_t)(s * A_COLS);
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {  // two K = 8 slices: +8 TMEM columns (A), +32 bytes = +2 encoded (B)
-          if (a.flags & 8) break;
-          const uint32_t acc = (t > 0 || ks > 0) ? 1u : 0u;
-          if (NSPLIT == 3) {
-            const uint64_t db_lo = make_desc_sw64(b_hi + b_slab);
-            umma_tf32_ts(tmem_base, ta_hi + 16 + 8 * ks, db_hi + 2 * ks, idesc, acc);  // lo * hi
-            umma_tf32_ts(tmem_base, ta_hi + 8 * ks, db_lo + 2 * ks, idesc, 1u);         // hi * lo
-            umma_tf32_ts(tmem_base, ta_hi + 8 * ks, db_hi + 2 * ks, idesc, 1u);         // hi * hi
-          } else {
-            umma_tf32_ts(tmem_base, ta_hi + 8 * ks, db_hi + 2 * ks, idesc, acc);
+          for (int ks = 0; ks < 2; ++ks) {  // two K = 8 slices: +8 TMEM columns (A), +32 bytes = +2 encoded (B)
+            const uint32_t acc = (t > 0 || ks > 0) ? 1u : 0u;
+            if (NSPLIT == 3) {
+              const uint64_t db_lo = make_desc_sw64(b_hi + b_slab);
+              umma_tf32_ts(tmem_base, ta_hi + 16 + 8 * ks, db_hi + 2 * ks, idesc, acc);  // lo * hi
+              umma_tf32_ts(tmem_base, ta_hi + 8 * ks, db_lo + 2 * ks, idesc, 1u);         // hi * lo
+              umma_tf32_ts(tmem_base, ta_hi + 8 * ks, db_hi + 2 * ks, idesc, 1u);         // hi * hi
+            } else {
+              umma_tf32_ts(tmem_base, ta_hi + 8 * ks, db_hi + 2 * ks, idesc, acc);
+            }
           }
+          umma_commit(empty_bar(s));                  // frees the A stage once the MMAs above have read it
+          if (recycle_b) umma_commit(bempty_bar(j));  // ... and the weight slot (only when the layer does not fit)
+          if (t == T - 1) umma_commit(tmem_full_bar);
         }
-        umma_commit(empty_bar(s));    // frees the A stage once the MMAs above have read it
-        if ((a.flags & 16) && blockIdx.x == 0 && t < 256) g_tc_debug[3][t] = clock64();
-        if (T > SB) umma_commit(bempty_bar(j));  // ... and the weight slot (only recycled when the layer does not fit)
+        __syncwarp();
         if (++s == S) {
           s = 0;
           ph ^= 1u;
@@ -439,15 +459,14 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
           bph ^= 1u;
         }
       }
-      umma_commit(tmem_full_bar);
     }
-    __syncwarp();
   } else {
-    // =========================== weight loader (one thread, TMA engine) ======================
-    if (lane == 0 && T > 0) {
+    // =========================== weight loader (TMA engine) ===================================
+    if (T > 0) {
       uint32_t km = kmask;
       int k = -1, c = nc, j = 0;
       uint32_t bph = 0;
+      const bool recycle_b = T > SB;
       for (int t = 0; t < T; ++t) {
         if (c == nc) {
           k = __ffs(km) - 1;
@@ -455,12 +474,15 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
           c = 0;
         }
         const int kw = a.k_reversed ? (K - 1 - k) : k;
-        mbar_wait(bempty_bar(j), bph ^ 1u);
-        const uint32_t b_hi = base + (uint32_t)j * b_slot;
-        const float* src = a.Bp + ((int64_t)kw * nc + c) * (int64_t)(a.c_out * 16);
-        mbar_arrive_expect_tx(bfull_bar(j), (uint32_t)b_slot);
-        bulk_g2s(b_hi, src, (uint32_t)b_slab, bfull_bar(j));
-        if (NSPLIT == 3) bulk_g2s(b_hi + b_slab, src + a.bp_half, (uint32_t)b_slab, bfull_bar(j));
+        if (recycle_b) mbar_wait(bempty_bar(j), bph ^ 1u);
+        if (elect_one()) {
+          const uint32_t b_hi = base + (uint32_t)j * b_slot;
+          const float* src = a.Bp + ((int64_t)kw * nc + c) * (int64_t)(a.c_out * 16);
+          mbar_arrive_expect_tx(bfull_bar(j), (uint32_t)b_slot);
+          bulk_g2s(b_hi, src, (uint32_t)b_slab, bfull_bar(j));
+          if (NSPLIT == 3) bulk_g2s(b_hi + b_slab, src + a.bp_half, (uint32_t)b_slab, bfull_bar(j));
+        }
+        __syncwarp();
         ++c;
         if (++j == SB) {
           j = 0;
@@ -468,7 +490,6 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
         }
       }
     }
-    __syncwarp();
   }
   __syncthreads();
   if (warp == 4) {
@@ -517,7 +538,7 @@ static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream) {
 
 // ws: packed weights, conv_tc_ws_bytes(K, c_in, c_out) bytes
 int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* dst, const int32_t* k_offsets,
-            float* out, int64_t n_out, int64_t max_pairs, int K, int c_in, int c_out, int wT, int krev, int nsplit,
+            const uint32_t* tile_mask, float* out, int64_t n_out, int64_t max_pairs, int K, int c_in, int c_out, int wT, int krev, int nsplit,
             bool pairs, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (ws_bytes < conv_tc_ws_bytes(K, c_in, c_out)) {
     set_error("conv_tc: workspace too small");
@@ -533,6 +554,7 @@ int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* d
   a.idx = idx;
   a.dst = dst;
   a.k_offsets = k_offsets;
+  a.tile_mask = (!pairs && K <= 32) ? tile_mask : nullptr;
   a.out = out;
   a.n_out = n_out;
   a.bp_half = half;
@@ -541,10 +563,6 @@ int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* d
   a.c_out = c_out;
   a.k_reversed = krev;
   a.stages = a.tmem_cols = a.a_col0 = a.sb = 0;
-  {
-    const char* e = getenv("B2S_TC_DEBUG");
-    a.flags = e ? atoi(e) : 0;
-  }
   if (!pairs) {
     int64_t gx = cdiv(n_out, TC_BM);
     return nsplit == 3 ? launch_tc<false, 3>(a, gx, stream) : launch_tc<false, 1>(a, gx, stream);
@@ -554,7 +572,3 @@ int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* d
 }
 
 }  // namespace b2s
-
-extern "C" int b2s_debug_tc_timeline(long long* host_out) {
-  return cudaMemcpyFromSymbol(host_out, b2s::g_tc_debug, sizeof(long long) * 4 * 256) == cudaSuccess ? 0 : -3;
-}

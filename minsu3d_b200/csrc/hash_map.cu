@@ -135,20 +135,35 @@ __global__ void __launch_bounds__(256) remap_vals_kernel(int n, int32_t* __restr
 __global__ void __launch_bounds__(256)
     kernel_map_kernel(const int4* __restrict__ out_coords, int64_t total, int K, int ksize, int dil,
                       const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals,
-                      uint64_t mask, int32_t* __restrict__ nbr) {
+                      uint64_t mask, int32_t* __restrict__ nbr, uint32_t* __restrict__ tile_mask) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  int o = (int)(t / K);
-  int kidx = (int)(t - (int64_t)o * K);
-  int ix = kidx % ksize;
-  int iy = (kidx / ksize) % ksize;
-  int iz = kidx / (ksize * ksize);
-  int lo = (ksize & 1) ? (ksize - 1) / 2 : 0;
-  int4 c = __ldg(out_coords + o);
-  int x = c.y + (ix - lo) * dil, y = c.z + (iy - lo) * dil, z = c.w + (iz - lo) * dil;
-  int r = -1;
-  if (coord_in_range(c.x, x, y, z)) r = hash_lookup(keys, vals, mask, pack_coord(c.x, x, y, z));
-  nbr[t] = r;
+  const bool valid = t < total;
+  int o = 0, kidx = 0, r = -1;
+  if (valid) {
+    o = (int)(t / K);
+    kidx = (int)(t - (int64_t)o * K);
+    int ix = kidx % ksize;
+    int iy = (kidx / ksize) % ksize;
+    int iz = kidx / (ksize * ksize);
+    int lo = (ksize & 1) ? (ksize - 1) / 2 : 0;
+    int4 c = __ldg(out_coords + o);
+    int x = c.y + (ix - lo) * dil, y = c.z + (iy - lo) * dil, z = c.w + (iz - lo) * dil;
+    if (coord_in_range(c.x, x, y, z)) r = hash_lookup(keys, vals, mask, pack_coord(c.x, x, y, z));
+    nbr[t] = r;
+  }
+  if (tile_mask != nullptr) {
+    // active-offset mask per 128-row tile (bit k set iff some row of the tile has a neighbour at offset k): a
+    // warp covers 32 consecutive (row, offset) entries, i.e. at most two tiles
+    const int tile = o >> 7;
+    const int tile0 = __shfl_sync(0xffffffffu, tile, 0);
+    const uint32_t bit = (valid && r >= 0) ? (1u << kidx) : 0u;
+    const uint32_t m0 = __reduce_or_sync(0xffffffffu, tile == tile0 ? bit : 0u);
+    const uint32_t m1 = __reduce_or_sync(0xffffffffu, tile != tile0 ? bit : 0u);
+    if ((threadIdx.x & 31) == 0) {
+      if (m0) atomicOr(tile_mask + tile0, m0);
+      if (m1) atomicOr(tile_mask + tile0 + 1, m1);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -271,7 +286,7 @@ int b2s_coord_unique(const int32_t* coords, int64_t n, int32_t quant, uint64_t* 
 
 int b2s_kernel_map(const int32_t* out_coords, int64_t n_out, int32_t ksize, int32_t dil,
                    const uint64_t* table_keys, const int32_t* table_vals, int64_t cap, int32_t* nbr,
-                   b2s_stream_t stream) {
+                   uint32_t* tile_mask, b2s_stream_t stream) {
   if (n_out < 0 || ksize < 1 || ksize > 7 || dil < 1 || (cap & (cap - 1)) != 0) {
     set_error("kernel_map: invalid argument");
     return B2S_E_INVALID;
@@ -279,8 +294,15 @@ int b2s_kernel_map(const int32_t* out_coords, int64_t n_out, int32_t ksize, int3
   if (n_out == 0) return B2S_OK;
   int K = ksize * ksize * ksize;
   int64_t total = n_out * K;
+  if (tile_mask != nullptr) {
+    if (K > 32) {
+      set_error("kernel_map: tile masks need ksize^3 <= 32");
+      return B2S_E_INVALID;
+    }
+    cudaMemsetAsync(tile_mask, 0, (size_t)cdiv(n_out, (int64_t)128) * 4, stream);
+  }
   kernel_map_kernel<<<(unsigned)cdiv(total, 256), 256, 0, stream>>>(
-      (const int4*)out_coords, total, K, ksize, dil, table_keys, table_vals, (uint64_t)cap - 1, nbr);
+      (const int4*)out_coords, total, K, ksize, dil, table_keys, table_vals, (uint64_t)cap - 1, nbr, tile_mask);
   return check_launch("kernel_map");
 }
 

@@ -84,16 +84,23 @@ def coord_pyramid(coords, base_stride, levels):
     return [(s, t, oc[:m]) for (s, t, oc), (m, _) in zip(out, counts)]
 
 
-def kernel_map(out_coords, table, ksize, dil):
-    """Output-stationary neighbour table nbr[n_out, ksize^3] (int32, -1 = no input)."""
+def kernel_map(out_coords, table, ksize, dil, with_tile_mask=False):
+    """Output-stationary neighbour table nbr[n_out, ksize^3] (int32, -1 = no input).
+
+    with_tile_mask: also return uint32-as-int32 [ceil(n_out / 128)] active-offset masks (bit k set iff some row of
+    the 128-row tile has a neighbour at offset k) that conv_table uses to skip empty offsets.
+    """
     require_cuda(out_coords)
     require(out_coords.dtype == I32 and out_coords.is_contiguous(), "out_coords must be contiguous int32")
     n_out = out_coords.size(0)
     K = ksize ** 3
     nbr = torch.empty((n_out, K), dtype=I32, device=out_coords.device)
+    tile_mask = None
+    if with_tile_mask and K <= 32:
+        tile_mask = torch.empty(((n_out + 127) // 128,), dtype=I32, device=out_coords.device)
     check(lib().b2s_kernel_map(ptr(out_coords), n_out, int(ksize), int(dil), ptr(table.keys), ptr(table.vals),
-                               table.cap, ptr(nbr), stream()), "kernel_map")
-    return nbr
+                               table.cap, ptr(nbr), ptr(tile_mask), stream()), "kernel_map")
+    return (nbr, tile_mask) if with_tile_mask else nbr
 
 
 def pairs_from_nbr(nbr, exact=False):
@@ -142,12 +149,12 @@ def _conv_ws(K, c_in, c_out, device):
     return workspace(lib().b2s_conv_ws_bytes(K, c_in, c_out), device)
 
 
-def conv_table(A, W, nbr, n_out, K, c_in, c_out, w_transposed=False, k_reversed=False, algo=None):
+def conv_table(A, W, nbr, n_out, K, c_in, c_out, w_transposed=False, k_reversed=False, algo=None, tile_mask=None):
     _f32c(A, "A")
     _f32c(W, "W")
     out = torch.empty((n_out, c_out), dtype=torch.float32, device=A.device)
     ws = _conv_ws(K, c_in, c_out, A.device)
-    check(lib().b2s_conv_table(ptr(A), ptr(W), ptr(nbr), ptr(out), n_out, K, c_in, c_out, int(w_transposed),
+    check(lib().b2s_conv_table(ptr(A), ptr(W), ptr(nbr), ptr(tile_mask), ptr(out), n_out, K, c_in, c_out, int(w_transposed),
                                int(k_reversed), _default_algo if algo is None else algo, ptr(ws), ws.numel(),
                                stream()), "conv_table")
     return out
