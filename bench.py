@@ -126,7 +126,7 @@ def dominant_kernel_roofline(data, device):
     hbm, bf16, which = _peaks()
     coords = data["voxel_xyz"]
     table, _, _, oc = ops.coord_unique(coords, 1)
-    nbr = ops.kernel_map(oc, table, 3, 1)
+    nbr, tile_mask = ops.kernel_map(oc, table, 3, 1, with_tile_mask=True)  # what the ME layer passes to every conv
     m = oc.size(0)
     pairs = int((nbr >= 0).sum().item())
     cin = cout = 16
@@ -136,13 +136,13 @@ def dominant_kernel_roofline(data, device):
 
     def timed(algo):
         for _ in range(3):
-            ops.conv_table(x, w, nbr, m, 27, cin, cout, algo=algo)
+            ops.conv_table(x, w, nbr, m, 27, cin, cout, algo=algo, tile_mask=tile_mask)
         times = []
         for _ in range(10):
             flush.zero_()  # L2 flush: 256 MB > 126 MB
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.conv_table(x, w, nbr, m, 27, cin, cout, algo=algo)
+            ops.conv_table(x, w, nbr, m, 27, cin, cout, algo=algo, tile_mask=tile_mask)
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1) * 1e-3)

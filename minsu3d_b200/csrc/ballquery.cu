@@ -20,6 +20,8 @@ constexpr int BQ_STEP = 16;    // per-cell window per merge round
 constexpr int BQ_CAND = 27 * BQ_STEP;
 constexpr int BQ_SORT = 512;   // >= BQ_CAND, power of two
 constexpr int BQ_WARPS = 8;
+constexpr int BQ_DENSE = 48;   // lists at least this long are emitted by the bitmap kernel instead of the merge ...
+constexpr int BQ_BM_WORDS = 2048;  // ... when their candidates span at most 65536 point indices (8 KB bitmap per warp)
 
 __device__ __forceinline__ uint64_t cell_key(int b, int cx, int cy, int cz) {
   const int bias = 1 << 17;
@@ -95,6 +97,22 @@ __device__ __forceinline__ bool in_ball(float ox, float oy, float oz, float4 c, 
   return d2 < r2;
 }
 
+// index span of a query's candidates in 32-bit words (cell lists are ascending: first / last entries bound it)
+__device__ __forceinline__ int cand_span(const float4* __restrict__ rec, CellRange cr, int* lo_word_out) {
+  int lo = 0x7fffffff, hi = -1;
+  if (cr.begin < cr.end) {
+    lo = __float_as_int(__ldg(&rec[cr.begin].w));
+    hi = __float_as_int(__ldg(&rec[cr.end - 1].w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  *lo_word_out = lo >> 5;
+  return (hi >> 5) - (lo >> 5) + 1;
+}
+
 // ---- count: one warp per query, lanes 0..26 own one cell each ------------------------------
 __global__ void __launch_bounds__(256)
     bq_count_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ batch_idxs, int n,
@@ -136,7 +154,7 @@ __global__ void __launch_bounds__(BQ_WARPS * 32)
                    double inv_cell, float r2, const float4* __restrict__ rec,
                    const uint64_t* __restrict__ tkeys, const int32_t* __restrict__ tstart,
                    const int32_t* __restrict__ tend, uint64_t mask,
-                   const int32_t* __restrict__ start_len, int32_t* __restrict__ idx) {
+                   const int32_t* __restrict__ start_len, int32_t* __restrict__ idx, int dense_min) {
   __shared__ int32_t s_cand[BQ_WARPS][BQ_CAND];
   __shared__ int32_t s_hit[BQ_WARPS][BQ_SORT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,6 +169,10 @@ __global__ void __launch_bounds__(BQ_WARPS * 32)
   CellRange cr{0, 0};
   if (lane < 27) cr = find_cell(tkeys, tstart, tend, mask,
                                 cell_key(b, cx + lane % 3 - 1, cy + (lane / 3) % 3 - 1, cz + lane / 9 - 1));
+  if (need >= dense_min) {  // long list: the bitmap kernel emits it unless its candidates span too many indices
+    int lw;
+    if (cand_span(rec, cr, &lw) <= BQ_BM_WORDS) return;
+  }
   int cur = cr.begin;
   const int end = cr.end;
   int32_t* cand = s_cand[warp];
@@ -237,6 +259,69 @@ __global__ void __launch_bounds__(BQ_WARPS * 32)
     for (int i = lane; i < w; i += 32) out[written + i] = hit[i];
     written += w;
     __syncwarp();
+  }
+}
+
+// ---- fill, dense lists: bitmap over the point-index range of the candidates -------------------
+// The output must be ascending in the point index and keep the LOWEST 1000 (bfs_cluster.cu:36-44).  For long
+// lists (shifted coordinates: hundreds of neighbours per point) sorting rounds dominate the merge above; here
+// every in-radius candidate sets one bit of a per-warp bitmap over [lowest, highest] candidate index (the cell
+// lists are ascending, so the bounds are their first / last entries) and the set bits are enumerated in order.
+__global__ void bq_fill_bitmap_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ batch_idxs, int n,
+                                      double inv_cell, float r2, const float4* __restrict__ rec,
+                                      const uint64_t* __restrict__ tkeys, const int32_t* __restrict__ tstart,
+                                      const int32_t* __restrict__ tend, uint64_t mask,
+                                      const int32_t* __restrict__ start_len, int32_t* __restrict__ idx,
+                                      int dense_min) {
+  extern __shared__ uint32_t s_bits[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= n) return;
+  const int need = start_len[2 * q + 1];
+  if (need < dense_min) return;
+  uint32_t* bm = s_bits + (size_t)warp * BQ_BM_WORDS;
+  int32_t* out = idx + start_len[2 * q];
+  const float ox = xyz[3 * q], oy = xyz[3 * q + 1], oz = xyz[3 * q + 2];
+  const int b = batch_idxs[q];
+  const int cx = cell_of(ox, inv_cell), cy = cell_of(oy, inv_cell), cz = cell_of(oz, inv_cell);
+  CellRange cr{0, 0};
+  if (lane < 27) cr = find_cell(tkeys, tstart, tend, mask,
+                                cell_key(b, cx + lane % 3 - 1, cy + (lane / 3) % 3 - 1, cz + lane / 9 - 1));
+  int lo_word;
+  const int nwords = cand_span(rec, cr, &lo_word);
+  if (nwords > BQ_BM_WORDS) return;  // handled by the merge kernel
+  for (int w = lane; w < nwords; w += 32) bm[w] = 0u;
+  __syncwarp();
+  for (int j = 0; j < 27; ++j) {
+    const int begin = __shfl_sync(0xffffffffu, cr.begin, j), end = __shfl_sync(0xffffffffu, cr.end, j);
+    for (int i = begin + lane; i < end; i += 32) {
+      const float4 r = __ldg(rec + i);
+      if (in_ball(ox, oy, oz, r, r2)) {
+        const int p = __float_as_int(r.w);
+        atomicOr(bm + ((p >> 5) - lo_word), 1u << (p & 31));
+      }
+    }
+  }
+  __syncwarp();
+  int written = 0;
+  for (int w0 = 0; w0 < nwords && written < need; w0 += 32) {
+    uint32_t word = (w0 + lane < nwords) ? bm[w0 + lane] : 0u;
+    const int cnt = __popc(word);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int pos = written + incl - cnt;
+    const int base_idx = (lo_word + w0 + lane) << 5;
+    while (word != 0u && pos < need) {
+      const int bit = __ffs(word) - 1;
+      word &= word - 1;
+      out[pos++] = base_idx + bit;
+    }
+    written += total;
   }
 }
 
@@ -350,9 +435,22 @@ int b2s_ballquery_fill(const float* xyz, const uint8_t* batch_idxs, const int32_
   }
   const double inv_cell = 1.0 / ((double)radius * (1.0 + 1e-5));
   const float r2 = radius * radius;
+  // long lists whose candidates span <= 65536 point indices are emitted by the bitmap kernel, the rest by the merge
+  const int dense_min = BQ_DENSE;
   bq_fill_kernel<<<(unsigned)cdiv(n, BQ_WARPS), BQ_WARPS * 32, 0, stream>>>(
       xyz, batch_idxs, (int)n, inv_cell, r2, w.rec, w.tkeys, w.tstart, w.tend, (uint64_t)w.cap - 1,
-      start_len, idx);
+      start_len, idx, dense_min);
+  {
+    const size_t smem = (size_t)BQ_WARPS * BQ_BM_WORDS * 4;
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(bq_fill_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = true;
+    }
+    bq_fill_bitmap_kernel<<<(unsigned)cdiv(n, BQ_WARPS), BQ_WARPS * 32, smem, stream>>>(
+        xyz, batch_idxs, (int)n, inv_cell, r2, w.rec, w.tkeys, w.tstart, w.tend, (uint64_t)w.cap - 1, start_len,
+        idx, dense_min);
+  }
   return check_launch("ballquery_fill");
 }
 

@@ -11,58 +11,62 @@
 namespace b2s {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_SLAB = 512;  // rows per CTA
 
 // partial[blk][2][c] (double): column sums of (p, q) where
-//   mode 0: p = x,            q = x*x
-//   mode 1: p = dy*mask(y),   q = dy*mask(y) * (x-mean)*rstd
-// Thread t owns the float4 column (t % c4) and the row phase (t / c4); four independent 16-byte
-// loads are in flight per thread and array, fp32 partials are flushed into double every 32 rows.
+//   MODE 0: p = x,            q = x*x
+//   MODE 1: p = dy*mask(y),   q = dy*mask(y) * (x-mean)*rstd
+// Thread t owns the float4 column (t % c4) and the row phase (t / c4); U independent 16-byte loads per array are in
+// flight per thread (8 for the statistics, 4 for the gradients), fp32 partials are flushed into double every 32
+// rows.  The kernel is latency-bound for the small tensors of the deep U-Net levels, so the launch geometry keeps
+// every thread at a handful of load batches: CTA b owns `chunk` consecutive rows (a multiple of the rows one batch
+// covers) and the grid is capped by bn_grid() so that the second stage (one CTA) stays short too.
 struct BnFinish {
-  // mode 0 (statistics): mean / var / rstd (+ running stats); mode 1 (gradients): dgamma / dbeta
+  // MODE 0 (statistics): mean / var / rstd (+ running stats); MODE 1 (gradients): dgamma / dbeta
   float eps, momentum;
   float *running_mean, *running_var, *out_a, *out_b, *out_c;  // stats: mean, var, rstd ; grads: dbeta, dgamma, -
   int32_t* counter;  // zero between launches: the last block to finish does the second stage and resets it
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
     bn_colsum_kernel(const float* __restrict__ x, const float* __restrict__ y,
                      const float* __restrict__ dy, const float* __restrict__ mean,
-                     const float* __restrict__ rstd, int64_t n, int c, int mode, int relu,
+                     const float* __restrict__ rstd, int64_t n, int c, int chunk, int relu,
                      double* __restrict__ partial, BnFinish fin) {
   extern __shared__ double s_acc[];  // [rpp][2][c]
+  constexpr int U = MODE == 0 ? 8 : 4;
   const int c4 = c >> 2;
   const int rpp = BN_THREADS / c4 > 0 ? BN_THREADS / c4 : 1;  // row phases per pass
-  const int64_t r0 = (int64_t)blockIdx.x * BN_SLAB;
-  const int64_t r1 = min(n, r0 + BN_SLAB);
+  const int64_t r0 = (int64_t)blockIdx.x * chunk;
+  const int64_t r1 = min(n, r0 + chunk);
   for (int vc = threadIdx.x % c4, ph = threadIdx.x / c4; vc < c4 && ph < rpp; vc += BN_THREADS) {
     double dp[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
     float p[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
     float4 m4 = make_float4(0, 0, 0, 0), rs4 = make_float4(1, 1, 1, 1);
-    if (mode == 1) {
+    if (MODE == 1) {
       m4 = __ldg((const float4*)mean + vc);
       rs4 = __ldg((const float4*)rstd + vc);
     }
     const float m[4] = {m4.x, m4.y, m4.z, m4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
     int cnt = 0;
-    for (int64_t r = r0 + ph; r < r1; r += 4 * (int64_t)rpp) {
-      float4 xv[4], gv[4], yv[4];
+    for (int64_t r = r0 + ph; r < r1; r += U * (int64_t)rpp) {
+      float4 xv[U], gv[MODE == 1 ? U : 1], yv[MODE == 1 ? U : 1];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         int64_t rr = r + (int64_t)u * rpp;
         bool ok = rr < r1;
         int64_t i = rr * c4 + vc;
         xv[u] = ok ? __ldg((const float4*)x + i) : make_float4(0, 0, 0, 0);
-        if (mode == 1) {
+        if (MODE == 1) {
           gv[u] = ok ? __ldg((const float4*)dy + i) : make_float4(0, 0, 0, 0);
           yv[u] = (ok && relu) ? __ldg((const float4*)y + i) : make_float4(1, 1, 1, 1);
           if (!ok) xv[u] = m4;  // (x - mean) = 0 for padding rows
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-        if (mode == 0) {
+        if (MODE == 0) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             p[j] += xs[j];
@@ -79,7 +83,8 @@ __global__ void __launch_bounds__(BN_THREADS)
           }
         }
       }
-      if (++cnt == 8) {  // 32 rows accumulated in fp32
+      cnt += U;
+      if (cnt == 32) {  // 32 rows accumulated in fp32
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           dp[j] += p[j]; dq[j] += q[j]; p[j] = 0.f; q[j] = 0.f;
@@ -118,11 +123,38 @@ __global__ void __launch_bounds__(BN_THREADS)
     const int ch = ch0 + threadIdx.x % (c < BN_THREADS ? c : BN_THREADS);
     const int g = threadIdx.x / (c < BN_THREADS ? c : BN_THREADS);
     double a = 0.0, b = 0.0;
-    if (ch < c && g < groups)
-      for (int blk = g; blk < nblk; blk += groups) {
-        a += __ldcg(partial + ((int64_t)blk * 2 + 0) * c + ch);
-        b += __ldcg(partial + ((int64_t)blk * 2 + 1) * c + ch);
+    if (ch < c && g < groups) {
+      // sixteen independent loads per array in flight (a one-by-one loop exposes an L2 round trip per block);
+      // the summation order stays fixed
+      int blk = g;
+      for (; blk + 15 * groups < nblk; blk += 16 * groups) {
+        double va[16], vb[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          va[u] = __ldcg(partial + ((int64_t)(blk + u * groups) * 2 + 0) * c + ch);
+          vb[u] = __ldcg(partial + ((int64_t)(blk + u * groups) * 2 + 1) * c + ch);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          a += va[u];
+          b += vb[u];
+        }
       }
+      {
+        double va[16], vb[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int bb = blk + u * groups;
+          va[u] = bb < nblk ? __ldcg(partial + ((int64_t)bb * 2 + 0) * c + ch) : 0.0;
+          vb[u] = bb < nblk ? __ldcg(partial + ((int64_t)bb * 2 + 1) * c + ch) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          a += va[u];
+          b += vb[u];
+        }
+      }
+    }
     __syncthreads();
     if (ch < c && g < groups) {
       s_acc[(g * 2 + 0) * c + ch] = a;
@@ -135,7 +167,7 @@ __global__ void __launch_bounds__(BN_THREADS)
         sp += s_acc[(h * 2 + 0) * c + ch];
         sq += s_acc[(h * 2 + 1) * c + ch];
       }
-      if (mode == 0) {
+      if (MODE == 0) {
         double m = sp / (double)n;
         double v = sq / (double)n - m * m;
         v = v > 0.0 ? v : 0.0;
@@ -213,9 +245,22 @@ using namespace b2s;
 
 extern "C" {
 
+// launch geometry of bn_colsum_kernel: rows per CTA (a multiple of the rows one load batch covers) and the grid
+static void bn_grid(int64_t n, int c, int unroll, int* chunk, int* nblk) {
+  const int c4 = c / 4;
+  const int rpp = BN_THREADS / c4 > 0 ? BN_THREADS / c4 : 1;
+  const int64_t batch_rows = (int64_t)rpp * unroll;
+  const int gmax = c <= 32 ? 296 : (c <= 64 ? 148 : 74);  // wide rows: fewer partials for the one-CTA second stage
+  int64_t want = cdiv(n > 0 ? n : 1, batch_rows);
+  int64_t g = want < gmax ? want : gmax;
+  int64_t ch = cdiv(cdiv(n > 0 ? n : 1, g), batch_rows) * batch_rows;
+  *chunk = (int)ch;
+  *nblk = (int)cdiv(n > 0 ? n : 1, ch);
+}
+
 size_t b2s_bn_ws_bytes(int64_t n, int32_t c) {
-  int64_t nblk = cdiv(n > 0 ? n : 1, BN_SLAB);
-  return align_up((size_t)nblk * 2 * c * 8) + 1024;
+  (void)n;
+  return align_up((size_t)296 * 2 * (c > 0 ? c : 4) * 8) + 1024;
 }
 
 static int bn_check(int64_t n, int32_t c) {
@@ -238,14 +283,16 @@ int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum
   int rc = bn_check(n, c);
   if (rc) return rc;
   if (n == 0) return B2S_OK;
-  int nblk = (int)cdiv(n, BN_SLAB);
+  int chunk, nblk;
+  bn_grid(n, c, 8, &chunk, &nblk);
   if (ws_bytes < (size_t)nblk * 2 * c * 8) {
     set_error("bn_stats: workspace too small");
     return B2S_E_WORKSPACE;
   }
   double* partial = (double*)ws;
   BnFinish fin{eps, momentum, running_mean, running_var, mean, var_biased, rstd, counter};
-  bn_colsum_kernel<<<nblk, BN_THREADS, bn_smem(c), stream>>>(x, nullptr, nullptr, nullptr, nullptr, n, c, 0, 0, partial, fin);
+  bn_colsum_kernel<0><<<nblk, BN_THREADS, bn_smem(c), stream>>>(x, nullptr, nullptr, nullptr, nullptr, n, c, chunk, 0,
+                                                               partial, fin);
   return check_launch("bn_stats");
 }
 
@@ -271,14 +318,15 @@ int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, 
     cudaMemsetAsync(dbeta, 0, (size_t)c * 4, stream);
     return check_launch("bn_backward(empty)");
   }
-  int nblk = (int)cdiv(n, BN_SLAB);
+  int chunk, nblk;
+  bn_grid(n, c, 4, &chunk, &nblk);
   if (ws_bytes < (size_t)nblk * 2 * c * 8) {
     set_error("bn_backward: workspace too small");
     return B2S_E_WORKSPACE;
   }
   double* partial = (double*)ws;
   BnFinish fin{0.f, 0.f, nullptr, nullptr, dbeta, dgamma, nullptr, counter};
-  bn_colsum_kernel<<<nblk, BN_THREADS, bn_smem(c), stream>>>(x, y, dy, mean, rstd, n, c, 1, relu, partial, fin);
+  bn_colsum_kernel<1><<<nblk, BN_THREADS, bn_smem(c), stream>>>(x, y, dy, mean, rstd, n, c, chunk, relu, partial, fin);
   int64_t total4 = n * (c / 4);
   bn_dx_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, stream>>>(
       (const float4*)x, (const float4*)y, (const float4*)dy, total4, c / 4, 1.0f / (float)n, mean, rstd,

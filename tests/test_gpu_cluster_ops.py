@@ -43,6 +43,26 @@ def test_ballquery_matches_oracle(n, collapse, radius):
         assert sl[:, 1].max() == 1000  # the cap (bfs_cluster.cu:38-43) is exercised
 
 
+def test_ballquery_dense_lists_with_scattered_indices():
+    """Long lists take the bitmap path only while their candidates span <= 65536 point indices; here two dense
+    blobs have their members scattered over a 70k-point scene (merge fallback) and one is index-local (bitmap)."""
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(99)
+    n = 70_000
+    xyz = (rng.random((n, 3)) * 6.0).astype(np.float32)  # sparse background
+    scattered = rng.choice(n, 1400, replace=False)
+    xyz[scattered[:700]] = (np.array([1.0, 1.0, 1.0]) + rng.standard_normal((700, 3)) * 0.008).astype(np.float32)
+    xyz[scattered[700:]] = (np.array([4.0, 2.0, 3.0]) + rng.standard_normal((700, 3)) * 0.02).astype(np.float32)
+    xyz[50_000:51_200] = (np.array([2.0, 5.0, 1.0]) + rng.standard_normal((1200, 3)) * 0.006).astype(np.float32)
+    bidx = np.zeros(n, np.uint8)
+    offs = np.array([0, n], np.int32)
+    idx, sl = oracle.ballquery(xyz, bidx, offs, 0.03)
+    assert sl[:, 1].max() == 1000 and np.count_nonzero(sl[:, 1] >= 48) > 2000
+    g_idx, g_sl = ops.ballquery(_dev(xyz), _dev(bidx), _dev(offs), 0.03)
+    assert np.array_equal(g_sl.cpu().numpy(), sl)
+    assert np.array_equal(g_idx.cpu().numpy(), idx)
+
+
 def test_ballquery_vs_reference_kernel(ref_ops):
     """The reference's CUDA kernel on the same GPU: identical per-point neighbour lists."""
     from minsu3d_b200 import ops
