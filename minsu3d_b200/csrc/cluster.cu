@@ -63,95 +63,130 @@ __device__ __forceinline__ int uf_find(int32_t* parent, int v) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) cc_init_kernel(int n, int32_t* __restrict__ parent) {
+// lastv[w] = largest listed index of a capped list (u is in list(w) iff u <= lastv[w] for u in radius), INT_MAX
+// for complete lists: one L2-resident read decides the symmetry of an edge instead of two dependent loads into
+// the big neighbour array.
+__global__ void __launch_bounds__(256)
+    cc_init_kernel(const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ start_len, int n,
+                   int32_t* __restrict__ root, int32_t* __restrict__ m, int32_t* __restrict__ lastv,
+                   uint8_t* __restrict__ asym) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < n) parent[v] = v;
+  if (v >= n) return;
+  root[v] = v;
+  m[v] = v;
+  asym[v] = 0;
+  const int s = __ldg(start_len + 2 * v), l = __ldg(start_len + 2 * v + 1);
+  lastv[v] = (l >= BQ_LIST_CAP) ? __ldg(nbr_idx + s + l - 1) : 0x7fffffff;
 }
 
+// one warp per node: union with the symmetric neighbours of higher index; nodes that own a directed-only edge
+// (u -> w with u not in list(w)) are flagged for the fixpoint below
 __global__ void __launch_bounds__(256)
     cc_hook_kernel(const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ start_len,
-                   const int16_t* __restrict__ labels, int n, int32_t* parent) {
+                   const int16_t* __restrict__ labels, const int32_t* __restrict__ lastv, int n, int32_t* root,
+                   uint8_t* __restrict__ asym, int* __restrict__ n_asym) {
   const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (u >= n) return;
   const int s = __ldg(start_len + 2 * u), l = __ldg(start_len + 2 * u + 1);
   const int lab = labels ? labels[u] : 0;
+  bool directed = false;
+  int ru_hint = uf_find(root, u);  // root of u as last seen by this lane
   for (int e = lane; e < l; e += 32) {
+    // (unrolling this loop for memory-level parallelism was measured slower: prefetched roots go stale and the
+    // shortcut below misses more often)
     const int w = __ldg(nbr_idx + s + e);
-    if (w <= u) continue;  // each undirected pair is handled from its lower endpoint
     if (labels && labels[w] != lab) continue;
-    const int lw = __ldg(start_len + 2 * w + 1);
-    if (lw >= BQ_LIST_CAP) {
-      // list(w) holds the LOWEST 1000 in-radius indices, and u is in radius of w (the predicate is
-      // symmetric), so u is listed iff it does not exceed the last (largest) listed index
-      if (u > __ldg(nbr_idx + __ldg(start_len + 2 * w) + lw - 1)) continue;
+    if (u > __ldg(lastv + w)) {  // list(w) is capped and does not reach up to u
+      directed = true;
+      continue;
     }
-    int ru = uf_find(parent, u), rw = uf_find(parent, w);
+    if (w <= u) continue;  // each undirected pair is handled from its lower endpoint
+    // dense blobs: after the first few unions nearly every neighbour already hangs under u's root
+    if (__ldcg(root + w) == ru_hint) continue;
+    int ru = uf_find(root, u), rw = uf_find(root, w);
+    ru_hint = min(ru, rw);
     while (ru != rw) {
       const int hi = max(ru, rw), lo = min(ru, rw);
-      const int old = atomicCAS(parent + hi, hi, lo);
+      const int old = atomicCAS(root + hi, hi, lo);
       if (old == hi) break;
-      ru = uf_find(parent, old);
+      ru = uf_find(root, old);
       rw = lo;
     }
   }
-}
-
-__global__ void __launch_bounds__(256) cc_compress_kernel(int n, int32_t* parent) {
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < n) {
-    int r = v, p = __ldcg(parent + r);
-    while (p != r) {
-      r = p;
-      p = __ldcg(parent + r);
-    }
-    parent[v] = r;
+  if (__any_sync(0xffffffffu, directed) && lane == 0) {
+    asym[u] = 1;
+    atomicAdd(n_asym, 1);
   }
 }
 
-// (1b) directed fixpoint
+__global__ void __launch_bounds__(256) cc_compress_kernel(int n, int32_t* root) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) {
+    int r = v, p = __ldcg(root + r);
+    while (p != r) {
+      r = p;
+      p = __ldcg(root + r);
+    }
+    root[v] = r;
+  }
+}
+
+// (1b) directed fixpoint on the contracted graph.  m[c] (c a union-find root) = lowest index that reaches
+// component c; only directed-only edges can lower it, and only flagged nodes own such edges, so a sweep reads
+// the lists of the flagged nodes instead of every edge.  Pointer jumping m[c] = m[root[m[c]]] is valid because
+// reachability is transitive.  Ends with comp[v] = m[root[v]].  Without truncated lists nothing is flagged and
+// the kernel only writes comp.
 __global__ void __launch_bounds__(CL_THREADS)
     cc_label_kernel(const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ start_len,
-                    const int16_t* __restrict__ labels, int n, int32_t* comp, unsigned* bar,
+                    const int16_t* __restrict__ labels, const int32_t* __restrict__ lastv,
+                    const int32_t* __restrict__ root, const uint8_t* __restrict__ asym,
+                    const int* __restrict__ n_asym, int n, int32_t* m, int32_t* __restrict__ comp, unsigned* bar,
                     int* flags) {
-  // comp arrives initialised with the union-find roots of the symmetric sub-graph (cc_hook_kernel)
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int gwarp = gtid >> 5, nwarps = nthreads >> 5;
-  int it = 0;
-  while (true) {
-    int* flag = flags + (it & 1);
-    for (int u = gwarp; u < n; u += nwarps) {
-      int cu = __ldcg(comp + u);
-      int s = __ldg(start_len + 2 * u), l = __ldg(start_len + 2 * u + 1);
-      int lab = labels ? labels[u] : 0;
-      bool ch = false;
-      for (int e = lane; e < l; e += 32) {
-        int w = __ldg(nbr_idx + s + e);
-        if (labels && labels[w] != lab) continue;
-        if (cu < __ldcg(comp + w)) {
-          int old = atomicMin(comp + w, cu);
-          ch |= (cu < old);
+  if (*n_asym > 0) {  // uniform across the grid (written by an earlier kernel)
+    int it = 0;
+    while (true) {
+      int* flag = flags + (it & 1);
+      for (int u = gwarp; u < n; u += nwarps) {
+        if (!asym[u]) continue;
+        const int cu = __ldcg(m + root[u]);
+        const int s = __ldg(start_len + 2 * u), l = __ldg(start_len + 2 * u + 1);
+        const int lab = labels ? labels[u] : 0;
+        bool ch = false;
+        for (int e = lane; e < l; e += 32) {
+          const int w = __ldg(nbr_idx + s + e);
+          if (labels && labels[w] != lab) continue;
+          if (u <= __ldg(lastv + w)) continue;  // symmetric edge: same component
+          const int rw = root[w];
+          if (cu < __ldcg(m + rw)) {
+            const int old = atomicMin(m + rw, cu);
+            ch |= (cu < old);
+          }
+        }
+        if (__any_sync(0xffffffffu, ch) && lane == 0) *flag = 1;
+      }
+      grid_sync(bar, gridDim.x);
+      if (gtid == 0) flags[(it + 1) & 1] = 0;
+      for (int v = gtid; v < n; v += nthreads) {
+        if (root[v] != v) continue;
+        const int c = __ldcg(m + v);
+        const int cc = __ldcg(m + root[c]);
+        if (cc < c) {
+          atomicMin(m + v, cc);
+          *flag = 1;
         }
       }
-      if (__any_sync(0xffffffffu, ch) && lane == 0) *flag = 1;
+      grid_sync(bar, gridDim.x);
+      const int changed = *((volatile int*)flag);
+      if (!changed) break;
+      ++it;
     }
-    grid_sync(bar, gridDim.x);
-    if (gtid == 0) flags[(it + 1) & 1] = 0;
-    for (int v = gtid; v < n; v += nthreads) {
-      int c = __ldcg(comp + v);
-      int cc = __ldcg(comp + c);
-      if (cc < c) {
-        atomicMin(comp + v, cc);
-        *flag = 1;
-      }
-    }
-    grid_sync(bar, gridDim.x);
-    int changed = *((volatile int*)flag);
-    if (!changed) break;
-    ++it;
   }
+  for (int v = gtid; v < n; v += nthreads) comp[v] = __ldcg(m + root[v]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -393,74 +428,77 @@ __global__ void __launch_bounds__(CL_THREADS) bfs_order_grid_kernel(GridOrderArg
   const int gtid = blockIdx.x * blockDim.x + tid, nthreads = G * blockDim.x;
   const int gwarp = gtid >> 5, nwarps = nthreads >> 5;
   const int n = a.n, nC = a.n_cluster;
+  // a.cid[v]: cluster id while v is unvisited, -1 outside the kept clusters, -2 - cluster id once visited: one
+  // read per edge decides "same cluster and unvisited" (members of a cluster share the seed's label, so the
+  // label needs no separate check).  a.parent[v]: queue position of the first frontier node that lists v.
+  int32_t* fstart = a.fstart;            // [2][n + 2] per-cluster start of the frontier, double-buffered per level
+  int32_t* filled = a.filled;            // [2][n + 2] nodes of the cluster already placed
+  const int fstride = n + 2;
 
   for (int v = gtid; v < n; v += nthreads) {
     a.seedcid[v] = -1;
-    a.pos[v] = -1;
     a.parent[v] = 0x7fffffff;
   }
   grid_sync(a.bar, G);
-  for (int c = gtid; c < nC; c += nthreads) {
-    int s = a.seeds[c];
-    a.seedcid[s] = c;
-    int off = a.cluster_offsets[c];
-    a.F0[c] = s;
-    a.pos[s] = off;
-    a.cluster_idxs[2 * off] = c;
-    a.cluster_idxs[2 * off + 1] = s;
-    a.filled[c] = 1;
-    a.fstart[c] = c;
-  }
-  if (gtid == 0) a.fstart[nC] = nC;
+  for (int c = gtid; c < nC; c += nthreads) a.seedcid[a.seeds[c]] = c;
+  if (gtid == 0) fstart[nC] = nC;
   grid_sync(a.bar, G);
   for (int v = gtid; v < n; v += nthreads) a.cid[v] = a.seedcid[a.comp[v]];
+  grid_sync(a.bar, G);
+  for (int c = gtid; c < nC; c += nthreads) {
+    const int sd = a.seeds[c];
+    const int off = a.cluster_offsets[c];
+    a.F0[c] = sd;
+    a.cid[sd] = -2 - c;
+    a.cluster_idxs[2 * off] = c;
+    a.cluster_idxs[2 * off + 1] = sd;
+    filled[c] = 1;
+    fstart[c] = c;
+  }
   grid_sync(a.bar, G);
 
   int32_t* F = a.F0;
   int32_t* Fn = a.F1;
   int fsize = nC;
+  int lvl = 0;
+  // Three device-wide barriers per level: A claim | B count (child side) | C scan + emit.
   while (fsize > 0) {
+    const int per = (fsize + G - 1) / G;  // frontier nodes per block (contiguous ranges)
+    const int32_t* fs_cur = fstart + (lvl & 1) * fstride;
+    const int32_t* fl_cur = filled + (lvl & 1) * fstride;
     // ---- A: every frontier node claims its unvisited neighbours (lowest queue position wins)
+    for (int bb = gtid; bb < G; bb += nthreads) a.blocksum[bb] = 0;
     for (int f = gwarp; f < fsize; f += nwarps) {
-      int u = F[f];
-      int cu = a.cid[u];
-      int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
-      int lab = a.labels ? a.labels[u] : 0;
-      for (int e = lane; e < l; e += 32) {
-        int w = __ldg(a.nbr_idx + s + e);
-        if (a.cid[w] != cu) continue;
-        if (a.labels && a.labels[w] != lab) continue;
-        if (__ldcg(a.pos + w) >= 0) continue;
-        atomicMin(a.parent + w, f);
+      const int u = F[f];
+      const int cu = -2 - a.cid[u];
+      const int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
+      if (lane == 0) a.cnt[f] = 0;
+      // four independent (neighbour -> state) load chains per lane: the loop is latency-bound otherwise
+      for (int e0 = lane; e0 < l; e0 += 128) {
+        int w[4], st[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = (e0 + 32 * k < l) ? __ldg(a.nbr_idx + s + e0 + 32 * k) : -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st[k] = (w[k] >= 0) ? __ldcg(a.cid + w[k]) : -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (w[k] >= 0 && st[k] == cu) atomicMin(a.parent + w[k], f);
       }
     }
     grid_sync(a.bar, G);
-    // ---- B: children per frontier node; frontier split into contiguous per-block ranges
-    const int per = (fsize + G - 1) / G;
+    // ---- B: children per frontier node, counted from the child side (one pass over the nodes, not the edges)
+    for (int v = gtid; v < n; v += nthreads) {
+      if (__ldcg(a.cid + v) < 0) continue;
+      const int f = __ldcg(a.parent + v);
+      if (f == 0x7fffffff) continue;
+      atomicAdd(a.cnt + f, 1);
+      atomicAdd(a.blocksum + f / per, 1);
+    }
+    grid_sync(a.bar, G);
+    // ---- C: exclusive scan of cnt over the block's frontier range (block prefix from blocksum), then emit the
+    // next frontier + final positions.  The only base value a block needs from outside its range is the one at
+    // the frontier start of the cluster that spans its first node: recomputed locally from blocksum and cnt.
     const int fb = min(fsize, (int)blockIdx.x * per), fe = min(fsize, fb + per);
-    int mysum = 0;
-    for (int f = fb + wib; f < fe; f += CL_THREADS / 32) {
-      int u = F[f];
-      int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
-      int c = 0;
-      for (int e0 = 0; e0 < l; e0 += 32) {
-        int e = e0 + lane;
-        bool child = false;
-        if (e < l) {
-          int w = __ldg(a.nbr_idx + s + e);
-          child = (__ldcg(a.parent + w) == f) && (__ldcg(a.pos + w) < 0);
-        }
-        c += __popc(__ballot_sync(0xffffffffu, child));
-      }
-      if (lane == 0) {
-        a.cnt[f] = c;
-        mysum += c;
-      }
-    }
-    int bsum = block_sum(mysum, s_red);
-    if (tid == 0) a.blocksum[blockIdx.x] = bsum;
-    grid_sync(a.bar, G);
-    // ---- C1: global exclusive scan of cnt -> base (block prefix from blocksum)
     int pre = 0, tot = 0;
     for (int b = tid; b < G; b += CL_THREADS) {
       int v = __ldcg(a.blocksum + b);
@@ -469,6 +507,18 @@ __global__ void __launch_bounds__(CL_THREADS) bfs_order_grid_kernel(GridOrderArg
     }
     pre = block_sum(pre, s_red);
     const int total = block_sum(tot, s_red);
+    int c0 = -1, c0_start = 0, c0_base = 0;
+    if (fb < fe) {
+      c0 = -2 - a.cid[F[fb]];
+      c0_start = fs_cur[c0];
+      if (c0_start < fb) {  // the cluster starts in an earlier block
+        const int b0 = c0_start / per;
+        int part = 0;
+        for (int b = tid; b < b0; b += CL_THREADS) part += __ldcg(a.blocksum + b);
+        for (int f = b0 * per + tid; f < c0_start; f += CL_THREADS) part += __ldcg(a.cnt + f);
+        c0_base = block_sum(part, s_red);
+      }
+    }
     int running = pre;
     for (int f0 = fb; f0 < fe; f0 += CL_THREADS) {
       int f = f0 + tid;
@@ -492,48 +542,57 @@ __global__ void __launch_bounds__(CL_THREADS) bfs_order_grid_kernel(GridOrderArg
       running += ctot;
     }
     if (blockIdx.x == 0 && tid == 0) a.base[fsize] = total;
-    grid_sync(a.bar, G);
-    // ---- C2: emit next frontier + final positions
+    __syncthreads();  // base[fb, fe) written by this block is read below
     for (int f = fb + wib; f < fe; f += CL_THREADS / 32) {
-      int u = F[f];
-      int c = a.cid[u];
-      int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
-      int cstart = __ldcg(a.base + a.fstart[c]);
-      int pbase = a.cluster_offsets[c] + a.filled[c] - cstart;
-      int j = __ldcg(a.base + f);
-      for (int e0 = 0; e0 < l; e0 += 32) {
-        int e = e0 + lane;
-        bool child = false;
-        int w = 0;
-        if (e < l) {
-          w = __ldg(a.nbr_idx + s + e);
-          child = (__ldcg(a.parent + w) == f) && (__ldcg(a.pos + w) < 0);
+      const int u = F[f];
+      const int c = -2 - a.cid[u];
+      const int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
+      const int fsc = fs_cur[c];
+      const int cstart = (fsc >= fb) ? a.base[fsc] : c0_base;  // fsc < fb only for c == c0
+      const int pbase = a.cluster_offsets[c] + fl_cur[c] - cstart;
+      int j = a.base[f];
+      for (int e0 = 0; e0 < l; e0 += 128) {
+        int w[4], pr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int e = e0 + 32 * k + lane;
+          w[k] = (e < l) ? __ldg(a.nbr_idx + s + e) : -1;
         }
-        unsigned m = __ballot_sync(0xffffffffu, child);
-        if (child) {
-          int jj = j + __popc(m & ((1u << lane) - 1));
-          Fn[jj] = w;
-          int p = pbase + jj;
-          a.pos[w] = p;
-          a.cluster_idxs[2 * p] = c;
-          a.cluster_idxs[2 * p + 1] = w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pr[k] = (w[k] >= 0) ? __ldcg(a.parent + w[k]) : -1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool child = (pr[k] == f) && (__ldcg(a.cid + w[k]) == c);  // pr == f implies w >= 0
+          const unsigned m = __ballot_sync(0xffffffffu, child);
+          if (child) {
+            const int jj = j + __popc(m & ((1u << lane) - 1));
+            Fn[jj] = w[k];
+            const int p = pbase + jj;
+            a.cluster_idxs[2 * p] = c;
+            a.cluster_idxs[2 * p + 1] = w[k];
+            a.cid[w[k]] = -2 - c;  // visited; only this warp sees parent[w] == f, so the race with readers is benign
+          }
+          j += __popc(m);
         }
-        j += __popc(m);
       }
     }
-    for (int c = gtid; c <= nC; c += nthreads) a.fnext[c] = __ldcg(a.base + a.fstart[c]);
     grid_sync(a.bar, G);
-    // ---- D: per-cluster bookkeeping (read again only in the next C2)
-    for (int c = gtid; c <= nC; c += nthreads) {
-      int fs = __ldcg(a.fnext + c);
-      if (c < nC) a.filled[c] += __ldcg(a.fnext + c + 1) - fs;
-      a.fstart[c] = fs;
+    // per-cluster bookkeeping for the next level (reads this level's buffers and base, writes the other halves;
+    // the next level's phase C reads them two barriers later)
+    {
+      int32_t* fs_nxt = fstart + ((lvl + 1) & 1) * fstride;
+      int32_t* fl_nxt = filled + ((lvl + 1) & 1) * fstride;
+      for (int c = gtid; c <= nC; c += nthreads) {
+        const int fsn = __ldcg(a.base + fs_cur[c]);
+        fs_nxt[c] = fsn;
+        if (c < nC) fl_nxt[c] = fl_cur[c] + __ldcg(a.base + fs_cur[c + 1]) - fsn;
+      }
     }
     int32_t* t = F;
     F = Fn;
     Fn = t;
     fsize = total;
-    // D's writes are ordered before the next C2 by the barriers of phases A and B
+    ++lvl;
   }
 }
 
@@ -713,18 +772,25 @@ int b2s_cluster_label(const int32_t* nbr_idx, const int32_t* start_len, const in
   if (n == 0) return B2S_OK;
   Workspace w(ws, ws_bytes);
   unsigned* bar = w.take<unsigned>(64);
-  if (!bar) {
+  int32_t* root = w.take<int32_t>(n);
+  int32_t* m = w.take<int32_t>(n);
+  int32_t* lastv = w.take<int32_t>(n);
+  uint8_t* asym = w.take<uint8_t>(n);
+  if (!bar || !asym) {
     set_error("cluster_label: workspace too small");
     return B2S_E_WORKSPACE;
   }
   int* flags = (int*)(bar + 2);
+  int* n_asym = (int*)(bar + 8);
   cudaMemsetAsync(bar, 0, 64 * 4, stream);
-  cc_init_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>((int)n, comp);
-  cc_hook_kernel<<<(unsigned)cdiv(n * 32, 256), 256, 0, stream>>>(nbr_idx, start_len, labels, (int)n, comp);
-  cc_compress_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>((int)n, comp);
+  cc_init_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(nbr_idx, start_len, (int)n, root, m, lastv, asym);
+  cc_hook_kernel<<<(unsigned)cdiv(n * 32, 256), 256, 0, stream>>>(nbr_idx, start_len, labels, lastv, (int)n, root, asym,
+                                                                  n_asym);
+  cc_compress_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>((int)n, root);
   int grid = coop_grid((const void*)cc_label_kernel, CL_THREADS, n * 32);
   int ni = (int)n;
-  void* args[] = {(void*)&nbr_idx, (void*)&start_len, (void*)&labels, (void*)&ni, (void*)&comp, (void*)&bar, (void*)&flags};
+  void* args[] = {(void*)&nbr_idx, (void*)&start_len, (void*)&labels, (void*)&lastv, (void*)&root, (void*)&asym,
+                  (void*)&n_asym, (void*)&ni,     (void*)&m,      (void*)&comp,  (void*)&bar,  (void*)&flags};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)cc_label_kernel, dim3(grid), dim3(CL_THREADS), args, 0, stream);
   if (e != cudaSuccess) {
     set_error(cudaGetErrorString(e));

@@ -26,3 +26,10 @@ for name, ms, r in log:
     if name == "ballquery": extra = "n=%d nActive=%d max_len=%d" % (r[1].size(0), r[0].numel(), int(r[1][:, 1].max()))
     if name == "cluster_extract": extra = "clusters=%d points=%d" % (r[1].numel() - 1, r[0].size(0))
     print("%-16s %7.3f ms  %s" % (name, ms, extra))
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    tr.step(data); torch.cuda.synchronize()
+print("-- clustering kernels in one step (us total / calls)")
+for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total):
+    if any(t in e.key for t in ("bq_", "cc_", "cl_", "bfs_", "cluster", "DeviceRadixSort", "DeviceScan", "ha_")):
+        print("%-60s %9.1f %4d" % (e.key[:60], e.device_time_total, e.count))
