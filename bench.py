@@ -175,7 +175,7 @@ def run_own(args):
     device = torch.device("cuda", local)
     _cabi.lib()
     cfg = models.Config.for_model("pointgroup", proposal_source="gt_noise")
-    trainer = train.Trainer(cfg, device)
+    trainer = train.Trainer(cfg, device, reserve_gb=16.0)  # of 180 GB: allocator never goes back to the driver
     n_pool = 3
     pool_host, pool_dev = [], []
     for i in range(n_pool):

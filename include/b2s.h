@@ -129,6 +129,11 @@ size_t b2s_bn_ws_bytes(int64_t n, int32_t c);
 int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum, float* running_mean,
                  float* running_var, float* mean, float* var_biased, float* rstd, int32_t* counter,
                  void* ws, size_t ws_bytes, b2s_stream_t stream);
+/* b2s_bn_stats followed by b2s_bn_apply in one call (training-mode forward of BatchNorm(+ReLU)). */
+int b2s_bn_forward(const float* x, int64_t n, int32_t c, float eps, float momentum,
+                   float* running_mean, float* running_var, const float* gamma, const float* beta,
+                   int32_t relu, float* y, float* mean, float* rstd, int32_t* counter,
+                   void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_bn_apply(const float* x, int64_t n, int32_t c, const float* mean, const float* rstd,
                  const float* gamma, const float* beta, int32_t relu, float* y, b2s_stream_t stream);
 /* backward of y = relu?(gamma*(x-mean)*rstd + beta) in training mode:

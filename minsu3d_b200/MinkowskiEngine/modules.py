@@ -251,11 +251,11 @@ class _BNReLU(torch.autograd.Function):
     def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, relu):
         x = x.contiguous()
         if training:
-            mean, rstd = ops.bn_stats(x, eps, momentum if running_mean is not None else 0.0, running_mean,
-                                      running_var)
+            y, mean, rstd = ops.bn_forward(x, eps, momentum if running_mean is not None else 0.0, running_mean,
+                                           running_var, weight, bias, relu)
         else:
             mean, rstd = running_mean, torch.rsqrt(running_var + eps)
-        y = ops.bn_apply(x, mean, rstd, weight, bias, relu)
+            y = ops.bn_apply(x, mean, rstd, weight, bias, relu)
         ctx.save_for_backward(x, y if relu else x, mean, rstd, weight)
         ctx.relu = relu
         ctx.training = training

@@ -296,6 +296,15 @@ int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum
   return check_launch("bn_stats");
 }
 
+int b2s_bn_forward(const float* x, int64_t n, int32_t c, float eps, float momentum, float* running_mean,
+                   float* running_var, const float* gamma, const float* beta, int32_t relu, float* y, float* mean,
+                   float* rstd, int32_t* counter, void* ws, size_t ws_bytes, b2s_stream_t stream) {
+  int rc = b2s_bn_stats(x, n, c, eps, momentum, running_mean, running_var, mean, nullptr, rstd, counter, ws, ws_bytes,
+                        stream);
+  if (rc) return rc;
+  return b2s_bn_apply(x, n, c, mean, rstd, gamma, beta, relu, y, stream);
+}
+
 int b2s_bn_apply(const float* x, int64_t n, int32_t c, const float* mean, const float* rstd,
                  const float* gamma, const float* beta, int32_t relu, float* y, b2s_stream_t stream) {
   int rc = bn_check(n, c);

@@ -55,6 +55,15 @@ class GradBucketer:
         if cur:
             self.buckets.append(cur)
         self.flats, self.bucket_of = [], {}
+        self._handles, self._hooks = [], []
+        self._ready, self._next = [], 0
+        self.launched_in_backward = 0
+        if self.world == 1:
+            # nothing to exchange: leave p.grad unset so that autograd hands its gradient tensors over without the
+            # accumulate-into-view kernel per parameter that the flat buckets cost
+            for p in self.params:
+                p.grad = None
+            return
         for bi, plist in enumerate(self.buckets):
             flat = torch.zeros(sum(p.numel() for p in plist), dtype=plist[0].dtype, device=plist[0].device)
             off = 0
@@ -75,6 +84,10 @@ class GradBucketer:
     # -- per step -----------------------------------------------------------------------------
     def zero_grad(self):
         """Keeps p.grad as views of the flat buckets (do not call optimizer.zero_grad(set_to_none=True))."""
+        if self.world == 1:
+            for p in self.params:
+                p.grad = None
+            return
         for flat in self.flats:
             flat.zero_()
         self._ready = [0] * len(self.buckets)
@@ -107,7 +120,7 @@ class GradBucketer:
             flat.mul_(inv)
 
     def grad_bytes(self):
-        return sum(f.numel() * f.element_size() for f in self.flats)
+        return sum(p.numel() * p.element_size() for p in self.params)
 
     def remove_hooks(self):
         for h in self._hooks:

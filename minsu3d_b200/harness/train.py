@@ -26,15 +26,27 @@ def host_bytes(data):
     return sum(v.numel() * v.element_size() for v in data.values() if torch.is_tensor(v))
 
 
+def reserve_device_pool(device, gigabytes):
+    """Grow torch's caching allocator once, up front: the step's ~800 allocations per iteration are then carved from
+    cached memory instead of occasionally reaching the driver (cuMemMap / cudaMalloc stalls of 10-100 ms when the
+    voxel count of a batch exceeds everything seen so far)."""
+    if device.type == "cuda" and gigabytes > 0:
+        block = torch.empty(int(gigabytes * 2 ** 30), dtype=torch.uint8, device=device)
+        del block
+
+
 class Trainer:
-    def __init__(self, cfg: models.Config, device, bucket_mb=8.0, seed=123):
+    def __init__(self, cfg: models.Config, device, bucket_mb=8.0, seed=123, reserve_gb=0.0):
         torch.manual_seed(seed)  # config/config.yaml:17
         self.cfg = cfg
         self.device = torch.device(device)
+        reserve_device_pool(self.device, reserve_gb)
         self.model = models.build_model(cfg).to(self.device)
         self.model.train()
         self.bucketer = dp.GradBucketer(self.model.parameters(), bucket_mb=bucket_mb)
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr)
+        # same update rule as the reference's torch.optim.Adam; the fused multi-tensor implementation keeps the
+        # host cost of the ~200-parameter step at a few launches (the default foreach path costs ~5 ms of Python)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr, fused=(self.device.type == "cuda"))
         self.last_losses = None
 
     def step(self, data):

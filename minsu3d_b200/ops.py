@@ -145,8 +145,15 @@ def _f32c(t, name):
     require(t.dtype == torch.float32 and t.is_contiguous(), "%s must be contiguous float32" % name)
 
 
+_CONV_WS_BYTES = {}
+
+
 def _conv_ws(K, c_in, c_out, device):
-    return workspace(lib().b2s_conv_ws_bytes(K, c_in, c_out), device)
+    key = (K, c_in, c_out)
+    nbytes = _CONV_WS_BYTES.get(key)
+    if nbytes is None:
+        nbytes = _CONV_WS_BYTES[key] = lib().b2s_conv_ws_bytes(K, c_in, c_out)
+    return workspace(nbytes, device)
 
 
 def conv_table(A, W, nbr, n_out, K, c_in, c_out, w_transposed=False, k_reversed=False, algo=None, tile_mask=None):
@@ -203,11 +210,30 @@ def bn_stats(x, eps=1e-5, momentum=0.0, running_mean=None, running_var=None):
     n, c = x.shape
     mean = torch.empty(c, dtype=torch.float32, device=x.device)
     rstd = torch.empty(c, dtype=torch.float32, device=x.device)
-    ws = workspace(lib().b2s_bn_ws_bytes(n, c), x.device)
+    ws = _bn_ws(c, x.device)
     check(lib().b2s_bn_stats(ptr(x), n, c, float(eps), float(momentum), ptr(running_mean), ptr(running_var),
                              ptr(mean), None, ptr(rstd), ptr(_bn_counter(x.device)), ptr(ws), ws.numel(), stream()),
           "bn_stats")
     return mean, rstd
+
+
+def _bn_ws(c, device):
+    # b2s_bn_ws_bytes does not depend on n (the grid of the column-sum kernel is capped): 296 * 2 * c doubles
+    return workspace(296 * 2 * max(int(c), 4) * 8 + 2048, device)
+
+
+def bn_forward(x, eps, momentum, running_mean, running_var, gamma, beta, relu):
+    """Training-mode BatchNorm(+ReLU) forward in one library call: returns (y, mean, rstd)."""
+    _f32c(x, "x")
+    n, c = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    mean, rstd = stats[0], stats[1]
+    ws = _bn_ws(c, x.device)
+    check(lib().b2s_bn_forward(ptr(x), n, c, float(eps), float(momentum), ptr(running_mean), ptr(running_var),
+                               ptr(gamma), ptr(beta), int(relu), ptr(y), ptr(mean), ptr(rstd),
+                               ptr(_bn_counter(x.device)), ptr(ws), ws.numel(), stream()), "bn_forward")
+    return y, mean, rstd
 
 
 def bn_apply(x, mean, rstd, gamma, beta, relu, out=None):
@@ -224,9 +250,9 @@ def bn_backward(x, y, dy, mean, rstd, gamma, relu, training):
     _f32c(dy, "dy")
     n, c = x.shape
     dx = torch.empty_like(x)
-    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
-    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
-    ws = workspace(lib().b2s_bn_ws_bytes(n, c), x.device)
+    dgb = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    dgamma, dbeta = dgb[0], dgb[1]
+    ws = _bn_ws(c, x.device)
     check(lib().b2s_bn_backward(ptr(x), ptr(y), ptr(dy), n, c, ptr(mean), ptr(rstd), ptr(gamma), int(relu),
                                 int(training), ptr(dx), ptr(dgamma), ptr(dbeta), ptr(_bn_counter(x.device)), ptr(ws),
                                 ws.numel(), stream()),
