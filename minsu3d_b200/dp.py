@@ -12,6 +12,11 @@ as (a) all of its gradients are ready and (b) every earlier bucket has been laun
 the collective order identical on all ranks even when a rank has unused parameters (e.g. the
 ScoreNet when a rank found no proposals).  NCCL runs the reduction on its own stream, overlapping
 the rest of backward; `finish()` launches whatever is left, waits, and averages.
+
+`overlap=False` ("pack after backward"): the ~30 MB all-reduce takes ~0.2 ms over NVLink/NVSwitch, far less than
+the host cost of ~200 Python hook calls and ~200 accumulate-into-view kernels per step, so on NVLink machines the
+trainer lets autograd hand over its gradient tensors untouched, packs them into the flat buckets with one
+multi-tensor copy per bucket after backward, all-reduces the buckets and points `p.grad` at the reduced views.
 """
 import os
 
@@ -38,8 +43,9 @@ def init_from_env(backend=None):
 
 
 class GradBucketer:
-    def __init__(self, params, bucket_mb=8.0, group=None):
+    def __init__(self, params, bucket_mb=8.0, group=None, overlap=True):
         self.group = group
+        self.overlap = overlap
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         params = [p for p in params if p.requires_grad]
         self.params = list(reversed(params))  # ~ order in which backward produces gradients
@@ -54,7 +60,7 @@ class GradBucketer:
             cur_n += p.numel()
         if cur:
             self.buckets.append(cur)
-        self.flats, self.bucket_of = [], {}
+        self.flats, self.views, self.bucket_of = [], [], {}
         self._handles, self._hooks = [], []
         self._ready, self._next = [], 0
         self.launched_in_backward = 0
@@ -67,16 +73,19 @@ class GradBucketer:
         for bi, plist in enumerate(self.buckets):
             flat = torch.zeros(sum(p.numel() for p in plist), dtype=plist[0].dtype, device=plist[0].device)
             off = 0
+            views = []
             for p in plist:
-                p.grad = flat[off:off + p.numel()].view_as(p)
+                views.append(flat[off:off + p.numel()].view_as(p))
+                p.grad = views[-1] if overlap else None
                 off += p.numel()
                 self.bucket_of[p] = bi
             self.flats.append(flat)
+            self.views.append(views)
         self._ready = [0] * len(self.buckets)
         self._next = 0
         self._handles = []
         self._hooks = []
-        if self.world > 1:
+        if self.world > 1 and overlap:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
         self.launched_in_backward = 0
@@ -84,9 +93,10 @@ class GradBucketer:
     # -- per step -----------------------------------------------------------------------------
     def zero_grad(self):
         """Keeps p.grad as views of the flat buckets (do not call optimizer.zero_grad(set_to_none=True))."""
-        if self.world == 1:
+        if self.world == 1 or not self.overlap:
             for p in self.params:
                 p.grad = None
+            self._handles = []
             return
         for flat in self.flats:
             flat.zero_()
@@ -109,6 +119,22 @@ class GradBucketer:
     def finish(self):
         """Launch the remaining buckets in order, wait for all of them, and average."""
         if self.world == 1:
+            return
+        if not self.overlap:
+            for flat, plist, views in zip(self.flats, self.buckets, self.views):
+                dst = [v for p, v in zip(plist, views) if p.grad is not None]
+                src = [p.grad for p in plist if p.grad is not None]
+                if len(dst) < len(plist):
+                    flat.zero_()  # parameters without a gradient on this rank contribute zeros
+                if dst:
+                    torch._foreach_copy_(dst, src)
+                self._handles.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            for h in self._handles:
+                h.wait()
+            torch._foreach_mul_(self.flats, 1.0 / self.world)
+            for plist, views in zip(self.buckets, self.views):
+                for p, v in zip(plist, views):
+                    p.grad = v
             return
         while self._next < len(self.buckets):
             self._launch(self._next)

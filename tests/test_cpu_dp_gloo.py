@@ -39,14 +39,14 @@ class _Net(torch.nn.Module):
         return out
 
 
-def _worker(rank, world, port, result_dir):
+def _worker(rank, world, port, result_dir, overlap=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     r, w, _ = dp.init_from_env(backend="gloo")
     assert (r, w) == (rank, world)
     torch.manual_seed(0)
     net = _Net()
-    bucketer = dp.GradBucketer(net.parameters(), bucket_mb=0.0005)  # tiny buckets -> several collectives
+    bucketer = dp.GradBucketer(net.parameters(), bucket_mb=0.0005, overlap=overlap)  # tiny buckets -> several collectives
     assert len(bucketer.buckets) >= 3
     g = torch.Generator().manual_seed(100 + rank)
     x = torch.randn(5, 8, generator=g)
@@ -61,9 +61,11 @@ def _worker(rank, world, port, result_dir):
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_world2_gloo(tmp_path):
+@pytest.mark.parametrize("overlap", [True, False])
+def test_bucketed_allreduce_world2_gloo(tmp_path, overlap):
     world, port = 2, _free_port()
-    mp.start_processes(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    mp.start_processes(_worker, args=(world, port, str(tmp_path), overlap), nprocs=world, join=True,
+                       start_method="spawn")
     res = [torch.load(os.path.join(tmp_path, "rank%d.pt" % r)) for r in range(world)]
     # reference: single-process gradients per rank, averaged
     torch.manual_seed(0)
@@ -81,6 +83,8 @@ def test_bucketed_allreduce_world2_gloo(tmp_path):
     assert torch.equal(res[0]["grads"]["a.weight"], res[1]["grads"]["a.weight"])
     # rank 1 never produced a gradient for the extra head: its bucket had to be launched from finish()
     assert res[1]["launched_in_backward"] <= res[0]["launched_in_backward"]
+    if not overlap:
+        assert res[0]["launched_in_backward"] == 0  # pack-after-backward mode: collectives only in finish()
 
 
 def test_single_process_bucketer_is_a_noop_wrapper():
