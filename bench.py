@@ -153,10 +153,17 @@ def dominant_kernel_roofline(data, device):
     # conv fwd bytes = 4*(M_in*Cin + M_out*Cout) + 4*P + 4*K*Cin*Cout ; flops = 2*P*Cin*Cout
     alg_bytes = 4 * (m * cin + m * cout) + 4 * pairs + 4 * 27 * cin * cout
     flops = 2.0 * pairs * cin * cout
-    return {"kernel": "conv_tc_kernel<false,3> + pack_weights_kernel (tcgen05 3xTF32 implicit GEMM, 3^3 conv 16->16 on the "
+    # DRAM traffic of the same launch from the committed `ncu --set full` capture of `bench.py --roofline-only`
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_tc_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    return {"traffic_source": traffic_src, "kernel": "conv_tc_kernel<false,3> + pack_weights_kernel (tcgen05 3xTF32 implicit GEMM, 3^3 conv 16->16 on the "
                       "level-0 map of the benchmark batch)",
             "bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": hbm, "unit": "GB/s",
-            "frac": alg_bytes / t / 1e9 / hbm, "traffic": None, "peak_source": which + " (burst copy)",
+            "frac": alg_bytes / t / 1e9 / hbm, "traffic": traffic, "peak_source": which + " (burst copy)",
             "us_per_launch": t * 1e6, "rows": m, "pairs": pairs, "algorithmic_bytes": alg_bytes,
             "useful_tflops": flops / t / 1e12, "dense_equivalent_tflops": 2.0 * m * 27 * cin * cout * 3 / t / 1e12,
             "fp32_fma_path_us": t_fma * 1e6,
@@ -264,7 +271,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--roofline-only", action="store_true",
+                    help="only the dominant-kernel measurement (the command the ncu captures in profiles/ profile)")
     args = ap.parse_args()
+    if args.roofline_only:
+        from minsu3d_b200.harness import scenes
+        device = torch.device("cuda", 0)
+        batch = scenes.make_batch(list(range(SCENES_PER_GPU)), device, POINTS_PER_SCENE)
+        print(json.dumps(dominant_kernel_roofline(batch, device)), flush=True)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:
