@@ -228,6 +228,21 @@ int b2s_global_avg_pool_bp(float* d_feats, const int32_t* offsets, const float* 
                            int32_t n_seg, int32_t c, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * clusters_voxelization (minsu3d/model/general_model.py:152-193) up to and
+ * including `clusters_coords.int()`, as one call: replaces three sec_* reductions, ~12 elementwise
+ * torch kernels and two index_selects.  Every float operation of the reference expression sequence
+ * keeps its own fp32 rounding, so the voxel coordinates are bit-identical.
+ *   clusters_idx  [sumNPoint, 2] (cluster id, point index), int32 or int64 (idx_is_int64)
+ *   clusters_offset [nCluster+1] int32 ; coords [N,3] float32 ; rand6 = the two torch.rand(3) draws (device)
+ *   out_xyz [sumNPoint, 4] int32 = (cluster id, x, y, z) -- the `batched_xyz` handed to sparse_quantize
+ *   cluster_params [nCluster, 8] float32 scratch/out: mean xyz, scale, offset xyz, unused
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_clusters_voxelize(const void* clusters_idx, int32_t idx_is_int64, const int32_t* clusters_offset,
+                          int64_t sum_npoint, int32_t n_cluster, const float* coords, float scale,
+                          int32_t spatial_shape, const float* rand6, int32_t* out_xyz,
+                          float* cluster_params, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * I1 / I2 -- proposal x instance IoU and mask labels (get_iou.cu:12-37,
  * cal_iou_and_masklabel.cu:14-140).  mask_scores == NULL: all proposal points count.
  * ---------------------------------------------------------------------------------------------- */

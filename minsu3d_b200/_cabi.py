@@ -59,6 +59,7 @@ _SIGNATURES = {
     "b2s_roipool_bp": (c_i32, [_P, _P, _P, _P, c_i32, c_i32, _P]),
     "b2s_global_avg_pool_fp": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
     "b2s_global_avg_pool_bp": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
+    "b2s_clusters_voxelize": (c_i32, [_P, c_i32, _P, c_i64, c_i32, _P, c_f32, c_i32, _P, _P, _P, _P]),
     "b2s_get_iou": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, _P]),
     "b2s_get_mask_label": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_f32, _P, _P, _P]),
 }
@@ -98,7 +99,7 @@ KERNELS_PER_CALL = {
     "b2s_scatter_add_rows": 1, "b2s_ballquery_count": 16, "b2s_ballquery_fill": 2, "b2s_cluster_label": 4,
     "b2s_cluster_select": 7, "b2s_cluster_order": 4, "b2s_cluster_centers": 1, "b2s_ha_assign": 1,
     "b2s_ha_concat": 4, "b2s_sec_mean": 1, "b2s_sec_min": 1, "b2s_sec_max": 1, "b2s_roipool_fp": 1,
-    "b2s_roipool_bp": 1, "b2s_global_avg_pool_fp": 1, "b2s_global_avg_pool_bp": 1, "b2s_get_iou": 1,
+    "b2s_roipool_bp": 1, "b2s_global_avg_pool_fp": 1, "b2s_global_avg_pool_bp": 1, "b2s_get_iou": 1, "b2s_clusters_voxelize": 2,
     "b2s_get_mask_label": 1,
 }
 _launches = [0]

@@ -253,6 +253,127 @@ __global__ void __launch_bounds__(256)
 
 static int seg_grid(int n_seg) { return n_seg < 8 * B2S_SM_COUNT ? n_seg : 8 * B2S_SM_COUNT; }
 
+
+// ------------------------------------------------------------------------------------------
+// clusters_voxelization (general_model.py:152-193) as two kernels: every float operation of the reference's
+// torch expression sequence is reproduced with its own rounding (no FMA contraction), so the integer voxel
+// coordinates are bit-identical:
+//   mean_c  = sec_mean(x)                      (sequential sum of x / count, sec_mean.cu:12-27)
+//   lo, hi  = min / max over the cluster of (x - mean_c)
+//   scale_c = min(1 / max_d((hi_d - lo_d) / S) - 0.01, scale)
+//   off_c,d = -(lo * scale) + max(S - (hi*scale - lo*scale) - 0.001, 0) * r0_d + min(S - (...) + 0.001, 0) * r1_d
+//   voxel   = int((x - mean_c) * scale_c + off_c)            (truncation, .int())
+// ------------------------------------------------------------------------------------------
+constexpr int CV_THREADS = 128;
+
+template <typename IdxT>
+__global__ void __launch_bounds__(CV_THREADS)
+    cv_cluster_kernel(const IdxT* __restrict__ clusters_idx, const int32_t* __restrict__ offsets, int n_cluster,
+                      const float* __restrict__ coords, float scale, float shape, const float* __restrict__ rnd,
+                      float* __restrict__ params /* [nC][8]: mean xyz, scale, offset xyz, - */) {
+  __shared__ float s_x[CV_THREADS * 3];
+  __shared__ float s_red[2][CV_THREADS / 32][3];
+  const int c = blockIdx.x;
+  if (c >= n_cluster) return;
+  const int b = offsets[c], e = offsets[c + 1];
+  const float count = (float)(e - b);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // (1) mean: points staged in shared memory CV_THREADS at a time, three threads add sequentially
+  float acc = 0.f;
+  for (int r0 = b; r0 < e; r0 += CV_THREADS) {
+    const int rows = min(CV_THREADS, e - r0);
+    if (tid < rows) {
+      const int64_t pt = (int64_t)clusters_idx[2 * (int64_t)(r0 + tid) + 1];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) s_x[tid * 3 + d] = __fdiv_rn(__ldg(coords + pt * 3 + d), count);
+    }
+    __syncthreads();
+    if (tid < 3)
+      for (int r = 0; r < rows; ++r) acc = __fadd_rn(acc, s_x[r * 3 + tid]);
+    __syncthreads();
+  }
+  __shared__ float s_mean[3];
+  if (tid < 3) s_mean[tid] = acc;
+  __syncthreads();
+  const float m0 = s_mean[0], m1 = s_mean[1], m2 = s_mean[2];
+  // (2) min / max of the centred coordinates (order-independent)
+  float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+  for (int r = b + tid; r < e; r += CV_THREADS) {
+    const int64_t pt = (int64_t)clusters_idx[2 * (int64_t)r + 1];
+    const float v[3] = {__fsub_rn(__ldg(coords + pt * 3), m0), __fsub_rn(__ldg(coords + pt * 3 + 1), m1),
+                        __fsub_rn(__ldg(coords + pt * 3 + 2), m2)};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = fminf(lo[d], v[d]);
+      hi[d] = fmaxf(hi[d], v[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+    if (lane == 0) {
+      s_red[0][warp][d] = lo[d];
+      s_red[1][warp][d] = hi[d];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float L[3], H[3];
+    for (int d = 0; d < 3; ++d) {
+      L[d] = s_red[0][0][d];
+      H[d] = s_red[1][0][d];
+      for (int w = 1; w < CV_THREADS / 32; ++w) {
+        L[d] = fminf(L[d], s_red[0][w][d]);
+        H[d] = fmaxf(H[d], s_red[1][w][d]);
+      }
+    }
+    // (3) scale and offset, one rounding per reference operation
+    // tensor / python-scalar on CUDA multiplies by the fp32 reciprocal of the scalar (ATen BinaryDivTrueKernel.cu)
+    const float inv_shape = __fdiv_rn(1.0f, shape);
+    float ext = __fmul_rn(__fsub_rn(H[0], L[0]), inv_shape);
+    ext = fmaxf(ext, __fmul_rn(__fsub_rn(H[1], L[1]), inv_shape));
+    ext = fmaxf(ext, __fmul_rn(__fsub_rn(H[2], L[2]), inv_shape));
+    float sc = __fsub_rn(__fdiv_rn(1.0f, ext), 0.01f);
+    sc = fminf(sc, scale);  // torch.clamp(max=scale)
+    float* out = params + (int64_t)c * 8;
+    out[0] = m0;
+    out[1] = m1;
+    out[2] = m2;
+    out[3] = sc;
+    for (int d = 0; d < 3; ++d) {
+      const float mn = __fmul_rn(L[d], sc), mx = __fmul_rn(H[d], sc);
+      const float rg = __fsub_rn(mx, mn);
+      const float room = __fsub_rn(shape, rg);
+      float off = __fadd_rn(-mn, __fmul_rn(fmaxf(__fsub_rn(room, 0.001f), 0.f), rnd[d]));
+      off = __fadd_rn(off, __fmul_rn(fminf(__fadd_rn(room, 0.001f), 0.f), rnd[3 + d]));
+      out[4 + d] = off;
+    }
+    out[7] = 0.f;
+  }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+    cv_point_kernel(const IdxT* __restrict__ clusters_idx, int64_t total, const float* __restrict__ coords,
+                    const float* __restrict__ params, int32_t* __restrict__ out_xyz) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t c = (int64_t)clusters_idx[2 * i], pt = (int64_t)clusters_idx[2 * i + 1];
+  const float4 p0 = __ldg((const float4*)(params + c * 8)), p1 = __ldg((const float4*)(params + c * 8 + 4));
+  const float mean[3] = {p0.x, p0.y, p0.z}, off[3] = {p1.x, p1.y, p1.z};
+  int v[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float x = __fsub_rn(__ldg(coords + pt * 3 + d), mean[d]);
+    v[d] = (int)__fadd_rn(__fmul_rn(x, p0.w), off[d]);  // float -> int32 conversion truncates like .int()
+  }
+  ((int4*)out_xyz)[i] = make_int4((int)c, v[0], v[1], v[2]);
+}
+
 }  // namespace b2s
 
 using namespace b2s;
@@ -367,6 +488,30 @@ int b2s_scatter_add_rows(const float* grad, const int64_t* idx, int64_t n, int32
     scatter_add_rows_scalar_kernel<<<(unsigned)cdiv(total, 256), 256, 0, stream>>>(grad, idx, total, c, gfeat);
   }
   return check_launch("scatter_add_rows");
+}
+
+int b2s_clusters_voxelize(const void* clusters_idx, int32_t idx_is_int64, const int32_t* clusters_offset,
+                          int64_t sum_npoint, int32_t n_cluster, const float* coords, float scale,
+                          int32_t spatial_shape, const float* rand6, int32_t* out_xyz, float* cluster_params,
+                          b2s_stream_t stream) {
+  if (sum_npoint < 0 || n_cluster < 0 || spatial_shape < 1) {
+    set_error("clusters_voxelize: invalid argument");
+    return B2S_E_INVALID;
+  }
+  if (sum_npoint == 0 || n_cluster == 0) return B2S_OK;
+  const float shape = (float)spatial_shape;
+  if (idx_is_int64) {
+    cv_cluster_kernel<int64_t><<<n_cluster, CV_THREADS, 0, stream>>>((const int64_t*)clusters_idx, clusters_offset,
+                                                                    n_cluster, coords, scale, shape, rand6, cluster_params);
+    cv_point_kernel<int64_t><<<(unsigned)cdiv(sum_npoint, 256), 256, 0, stream>>>(
+        (const int64_t*)clusters_idx, sum_npoint, coords, cluster_params, out_xyz);
+  } else {
+    cv_cluster_kernel<int32_t><<<n_cluster, CV_THREADS, 0, stream>>>((const int32_t*)clusters_idx, clusters_offset,
+                                                                    n_cluster, coords, scale, shape, rand6, cluster_params);
+    cv_point_kernel<int32_t><<<(unsigned)cdiv(sum_npoint, 256), 256, 0, stream>>>(
+        (const int32_t*)clusters_idx, sum_npoint, coords, cluster_params, out_xyz);
+  }
+  return check_launch("clusters_voxelize");
 }
 
 }  // extern "C"

@@ -157,14 +157,11 @@ class Config:
         return Config(**base)
 
 
-def clusters_voxelization(clusters_idx, clusters_offset, feats, coords, scale, spatial_shape, rand=None):
-    """general_model.py:152-193.  `rand` ([2,3] tensor) replaces the two torch.rand(3) draws so that
-    parity runs can share them."""
-    device = feats.device
+def clusters_voxel_coords_torch(clusters_idx, clusters_offset, coords, scale, spatial_shape, rand):
+    """The reference's torch expression sequence (general_model.py:154-184) up to `batched_xyz`: kept as the
+    restatement the fused kernel is checked against (tests/test_gpu_cluster_ops.py)."""
     batch_idx = clusters_idx[:, 0]
-    c_idxs = clusters_idx[:, 1]
-    feats = feats[c_idxs]
-    cc = coords[c_idxs].contiguous()
+    cc = coords[clusters_idx[:, 1]].contiguous()
     mean = common_ops.sec_mean(cc, clusters_offset)
     cc = cc - torch.index_select(mean, 0, batch_idx)
     cmin = common_ops.sec_min(cc, clusters_offset)
@@ -174,13 +171,21 @@ def clusters_voxelization(clusters_idx, clusters_offset, feats, coords, scale, s
     min_xyz, max_xyz = cmin * cscale[:, None], cmax * cscale[:, None]
     cc = cc * torch.index_select(cscale, 0, batch_idx)[:, None]
     rng = max_xyz - min_xyz
-    if rand is None:
-        rand = torch.rand(2, 3, device=device)
     offset = -min_xyz + torch.clamp(spatial_shape - rng - 0.001, min=0) * rand[0]
     offset = offset + torch.clamp(spatial_shape - rng + 0.001, max=0) * rand[1]
     cc = cc + torch.index_select(offset, 0, batch_idx)
     cc = cc.int()
-    batched_xyz = torch.cat((clusters_idx[:, 0].unsqueeze(-1).to(cc.dtype), cc), dim=1)
+    return torch.cat((clusters_idx[:, 0].unsqueeze(-1).to(cc.dtype), cc), dim=1)
+
+
+def clusters_voxelization(clusters_idx, clusters_offset, feats, coords, scale, spatial_shape, rand=None):
+    """general_model.py:152-193 with the coordinate part fused into one library call.  `rand`
+    ([2,3] tensor) replaces the two torch.rand(3) draws so that parity runs can share them (appendix C.11)."""
+    device = feats.device
+    feats = feats[clusters_idx[:, 1]]
+    if rand is None:
+        rand = torch.rand(2, 3, device=device)
+    batched_xyz = ops.clusters_voxelize(clusters_idx.contiguous(), clusters_offset, coords, scale, spatial_shape, rand)
     voxel_xyz, voxel_features, _, voxel_point_map = ME.utils.sparse_quantize(
         batched_xyz, feats, return_index=True, return_inverse=True, device="cuda")
     return ME.SparseTensor(features=voxel_features, coordinates=voxel_xyz, device=device), voxel_point_map

@@ -439,3 +439,27 @@ def get_mask_label(proposals_idx, proposals_offset, instance_labels, instance_cl
 
 
 __all__ = [n for n in dir() if not n.startswith("_")]
+
+
+# ------------------------------------------------------------------------------------------
+# clusters_voxelization up to `.int()` (general_model.py:152-182)
+# ------------------------------------------------------------------------------------------
+def clusters_voxelize(clusters_idx, clusters_offset, coords, scale, spatial_shape, rand):
+    """Integer voxel coordinates [sumNPoint, 4] = (cluster id, x, y, z) of every proposal point.
+
+    clusters_idx [S, 2] int32/int64, clusters_offset [nC+1] int32, coords [N, 3] float32, rand [2, 3] float32 (the
+    two torch.rand(3) draws of the reference).  Bit-identical to the reference's torch expression sequence.
+    """
+    require_cuda(clusters_idx, clusters_offset, coords, rand)
+    require(clusters_idx.dim() == 2 and clusters_idx.size(1) == 2 and clusters_idx.is_contiguous()
+            and clusters_idx.dtype in (torch.int32, torch.int64), "clusters_idx must be contiguous int32/int64 [S, 2]")
+    require(clusters_offset.dtype == I32 and clusters_offset.is_contiguous(), "clusters_offset must be int32")
+    _f32c(coords, "coords")
+    rand = rand.to(torch.float32).contiguous()
+    s_total, n_cluster = clusters_idx.size(0), clusters_offset.numel() - 1
+    out = torch.empty((s_total, 4), dtype=I32, device=coords.device)
+    params = torch.empty((max(n_cluster, 1), 8), dtype=torch.float32, device=coords.device)
+    check(lib().b2s_clusters_voxelize(ptr(clusters_idx), int(clusters_idx.dtype == torch.int64), ptr(clusters_offset),
+                                      s_total, n_cluster, ptr(coords), float(scale), int(spatial_shape), ptr(rand),
+                                      ptr(out), ptr(params), stream()), "clusters_voxelize")
+    return out

@@ -253,3 +253,13 @@ def convT_fwd(feats_coarse, W, nbr_down, n_fine):
     out = np.zeros((n_fine, cout), np.float32)
     lib().orc_convT_fwd(_p(feats_coarse), _p(W), _p(nbr_down), _p(out), n_fine, feats_coarse.shape[0], K, cin, cout)
     return out
+
+
+def clusters_voxelize(clusters_idx, clusters_offset, coords, scale, spatial_shape, rand):
+    """general_model.py:152-182: integer voxel coordinates [sumNPoint, 4] = (cluster id, x, y, z)."""
+    idx, offs = _c(clusters_idx, np.int64), _c(clusters_offset, np.int32)
+    coords, rand = _c(coords, np.float32), _c(rand, np.float32)
+    out = np.zeros((idx.shape[0], 4), np.int32)
+    lib().orc_clusters_voxelize(_p(idx), _p(offs), idx.shape[0], offs.shape[0] - 1, _p(coords),
+                                ctypes.c_float(scale), int(spatial_shape), _p(rand), _p(out))
+    return out

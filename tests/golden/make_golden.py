@@ -131,11 +131,53 @@ def gpu_goldens(ref, path):
     print("wrote", path)
 
 
+def gpu_golden_clusters_voxelize(ref, path):
+    """The reference's torch expression sequence of clusters_voxelization (general_model.py:154-184) executed on the
+    GPU with the reference's own sec_mean / sec_min / sec_max kernels (the function itself cannot be imported: its
+    module imports MinkowskiEngine)."""
+    rng = np.random.default_rng(777)
+    n, n_cluster, scale, shape = 30_000, 48, 50, 14
+    coords = (rng.random((n, 3)) * 8.0).astype(np.float32)
+    sizes = rng.integers(1, 1500, n_cluster)
+    sizes[0] = 1
+    offs = np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
+    pts = np.concatenate([rng.integers(0, n, 1) + rng.integers(0, 300, s) for s in sizes]) % n
+    idx = np.stack((np.repeat(np.arange(n_cluster), sizes), pts), 1).astype(np.int64)
+    rand = rng.random((2, 3)).astype(np.float32)
+    d = lambda a: t(a).cuda()  # noqa: E731
+    clusters_idx, clusters_offset, dcoords, drand = d(idx), d(offs), d(coords), d(rand)
+
+    def sec(kind, x):
+        o = torch.zeros((n_cluster, 3), device="cuda")
+        getattr(ref, "sec_" + kind)(x.contiguous(), clusters_offset, o, n_cluster, 3)
+        return o
+
+    batch_idx = clusters_idx[:, 0]
+    cc = dcoords[clusters_idx[:, 1]]
+    mean = sec("mean", cc)
+    cc = cc - torch.index_select(mean, 0, batch_idx)
+    cmin, cmax = sec("min", cc), sec("max", cc)
+    cscale = 1 / ((cmax - cmin) / shape).max(1)[0] - 0.01
+    cscale = torch.clamp(cscale, min=None, max=scale)
+    min_xyz, max_xyz = cmin * cscale[:, None], cmax * cscale[:, None]
+    cc = cc * torch.index_select(cscale, 0, batch_idx)[:, None]
+    rg = max_xyz - min_xyz
+    offset = -min_xyz + torch.clamp(shape - rg - 0.001, min=0) * drand[0]
+    offset += torch.clamp(shape - rg + 0.001, max=0) * drand[1]
+    cc = cc + torch.index_select(offset, 0, batch_idx)
+    cc = cc.int()
+    batched = torch.cat((clusters_idx[:, 0].unsqueeze(-1).int(), cc), dim=1)
+    np.savez_compressed(path, idx=idx, offs=offs, coords=coords, rand=rand, scale=np.float32(scale),
+                        shape=np.int32(shape), batched_xyz=batched.cpu().numpy())
+    print("wrote", path)
+
+
 if __name__ == "__main__":
     ref = build_ref.load()
     assert ref is not None, "build oracle/_ref first (python oracle/build_ref.py)"
     if "--gpu" in sys.argv:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         gpu_goldens(ref, os.path.join(ROOT, "gpurun_out", "golden_gpu.npz"))
+        gpu_golden_clusters_voxelize(ref, os.path.join(ROOT, "gpurun_out", "golden_clusters_voxelize_gpu.npz"))
     else:
         cpu_goldens(ref)

@@ -88,6 +88,15 @@ def test_oracle_matches_reference_cuda_kernel_goldens():
     assert np.array_equal(ml, g["mask_label"]) and np.array_equal(mm, g["mask_label_mask"])
 
 
+def test_oracle_clusters_voxelize_matches_gpu_golden():
+    """tests/golden/clusters_voxelize_gpu.npz = the reference's torch expression sequence (general_model.py:154-184)
+    run on a B200 with the reference's own sec_* kernels (make_golden.py --gpu)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "clusters_voxelize_gpu.npz"))
+    got = oracle.clusters_voxelize(g["idx"], g["offs"], g["coords"], float(g["scale"]), int(g["shape"]), g["rand"])
+    assert np.array_equal(got, g["batched_xyz"])
+    assert got[:, 1:].min() >= 0 and got[:, 1:].max() <= int(g["shape"])
+
+
 # ------------------------------------------------------------------------------------------------
 # MinkowskiEngine restatement: C oracle vs dictionary restatement vs dense torch conv3d
 # ------------------------------------------------------------------------------------------------

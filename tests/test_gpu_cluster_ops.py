@@ -313,3 +313,29 @@ def test_iou_and_mask_label_bit_exact(ref_ops):
         r_mm = torch.zeros(pidx.size, dtype=torch.bool, device="cuda")
         ref_ops.get_mask_label(d[0], d[1], d[2], _dev(cls), iou, inst_num.size, offs.size - 1, -1, thr, r_ml, r_mm)
         assert torch.equal(r_ml, ml) and torch.equal(r_mm, mm)
+
+
+# ---- clusters_voxelization ---------------------------------------------------
+@pytest.mark.parametrize("n_cluster,scale,shape,idx_dtype", [(1, 50, 14, torch.int64), (37, 50, 14, torch.int64),
+                                                             (200, 50, 14, torch.int32), (60, 5, 20, torch.int64)])
+def test_clusters_voxelize_bit_exact(n_cluster, scale, shape, idx_dtype):
+    """Fused kernel == the reference's torch expression sequence on the GPU == the C oracle, integer for integer."""
+    from minsu3d_b200 import ops
+    from minsu3d_b200.harness import models
+    rng = np.random.default_rng(5 + n_cluster)
+    n = 60_000
+    coords = (rng.random((n, 3)) * 8.0).astype(np.float32)
+    sizes = rng.integers(1, 3000, n_cluster)
+    sizes[0] = 1  # a single-point cluster: extent 0 -> 1/0 = inf, clamped to `scale`
+    offs = np.concatenate(([0], np.cumsum(sizes))).astype(np.int32)
+    pts = np.concatenate([rng.integers(0, n, 1) + rng.integers(0, 400, s) % n for s in sizes]) % n  # local blobs
+    cid = np.repeat(np.arange(n_cluster), sizes)
+    idx = np.stack((cid, pts), 1).astype(np.int64)
+    rand = rng.random((2, 3)).astype(np.float32)
+    want = oracle.clusters_voxelize(idx, offs, coords, float(scale), shape, rand)
+    d_idx = _dev(idx).to(idx_dtype)
+    got = ops.clusters_voxelize(d_idx, _dev(offs), _dev(coords), scale, shape, _dev(rand))
+    seq = models.clusters_voxel_coords_torch(_dev(idx), _dev(offs), _dev(coords), scale, shape, _dev(rand))
+    assert np.array_equal(got.cpu().numpy(), seq.cpu().numpy())
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert got[:, 1:].min() >= 0 and got[:, 1:].max() < shape + 1
