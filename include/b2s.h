@@ -175,7 +175,10 @@ int b2s_ballquery_fill(const float* xyz, const uint8_t* batch_idxs, const int32_
  *
  * b2s_cluster_label : comp[v] = lowest index that reaches v (labels == NULL: no label test).
  * b2s_cluster_select: sizes, keep mask, compaction.  mode 0: keep size >= thr_i (pg);
- *     mode 1: keep (float)size >= thr_f (sg).  mode 2 (HAIS): class thresholds from
+ *     mode 1: keep (float)size >= thr_f (sg).  mode 3: mode 1 with one threshold per class,
+ *     keep (float)size >= point_num_avg[labels[seed]] (all SoftGroup classes clustered in one call:
+ *     the caller stacks the per-class point sets and gives each class its own batch indices).
+ *     mode 2 (HAIS): class thresholds from
  *     point_num_avg; cls: 0 = dropped, 1 = kept fragment, 2 = primary; fragments (size < high)
  *     are also listed when want_fragments.
  *     Outputs: d_count = {nCluster, sumNPoint}, cluster_offsets [nCluster+1], seeds [nCluster].

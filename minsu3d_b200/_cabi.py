@@ -134,12 +134,15 @@ def ptr(t):
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_get_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
 
 
 def stream():
     """Raw cudaStream_t of torch's current stream on the current device (fast path: ~0.3 us)."""
     if _raw_stream is not None:
-        return _raw_stream(torch.cuda.current_device())
+        # torch._C._cuda_getDevice skips torch.cuda.current_device()'s lazy-init checks (~1.2 us per call, called
+        # about twice per library call)
+        return _raw_stream(_get_device())
     return torch.cuda.current_stream().cuda_stream
 
 

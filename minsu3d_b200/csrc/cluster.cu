@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(256)
   if (comp[v] == v) {
     if (mode == 0) keep = sz >= thr_i;
     else if (mode == 1) keep = (float)sz >= thr_f;  // bfs_cluster.cpp:116-121 (int compared as float)
+    else if (mode == 3) keep = (float)sz >= point_num_avg[labels[v]];  // mode 1 with one threshold per class
     else {
       // hierarchical_aggregation.cpp:58-74: double literal x float mean, rounded into float
       float mean = point_num_avg[labels[v]];
@@ -803,7 +804,7 @@ int b2s_cluster_select(const int32_t* comp, const int16_t* labels, int64_t n, in
                        int32_t thr_i, float thr_f, const float* point_num_avg, int32_t group,
                        int32_t* cluster_offsets, int32_t* seeds, int32_t* d_count, void* ws,
                        size_t ws_bytes, b2s_stream_t stream) {
-  if (n < 0 || mode < 0 || mode > 2 || (mode == 2 && (!labels || !point_num_avg))) {
+  if (n < 0 || mode < 0 || mode > 3 || (mode >= 2 && (!labels || !point_num_avg))) {
     set_error("cluster_select: invalid argument");
     return B2S_E_INVALID;
   }

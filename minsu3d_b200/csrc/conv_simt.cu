@@ -179,8 +179,9 @@ __global__ void __launch_bounds__(WG_THREADS)
   constexpr int NT = (BA / TA) * (BG / TG);  // threads covering the tile once
   constexpr int NG = WG_THREADS / NT;        // pair-splitting groups
   static_assert(NG >= 1 && NG * NT == WG_THREADS, "bad wgrad tiling");
-  __shared__ __align__(16) float As[WG_PC][BA + 4];
-  __shared__ __align__(16) float Gs[WG_PC][BG + 4];
+  __shared__ __align__(16) float s_stage[WG_PC * (BA + 4) + WG_PC * (BG + 4)];
+  float (*As)[BA + 4] = (float (*)[BA + 4])s_stage;
+  float (*Gs)[BG + 4] = (float (*)[BG + 4])(s_stage + WG_PC * (BA + 4));
   __shared__ int s_cum[130];  // cumulative chunk counts per k (K <= 125)
   __shared__ int s_koff[130];
 
@@ -210,8 +211,31 @@ __global__ void __launch_bounds__(WG_THREADS)
 #pragma unroll
     for (int j = 0; j < TG; ++j) acc[i][j] = 0.f;
 
+  // flush: the NG pair-splitting groups hold partial sums of the same BA x BG tile; they are combined through
+  // shared memory (reusing the staging buffers) so that one atomicAdd per tile element leaves the CTA instead of NG
   auto flush = [&](int k) {
     float* base = gW + (int64_t)k * c_a * c_g;
+    if (NG > 1 && NG * BA * BG <= WG_PC * (BA + 4) + WG_PC * (BG + 4)) {
+      float* red = &As[0][0];  // As and Gs are adjacent static arrays; NG*BA*BG floats fit (checked above)
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < TA; ++i)
+#pragma unroll
+        for (int j = 0; j < TG; ++j) {
+          red[(grp * BA + ta * TA + i) * BG + tg * TG + j] = acc[i][j];
+          acc[i][j] = 0.f;
+        }
+      __syncthreads();
+      for (int e = tid; e < BA * BG; e += WG_THREADS) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < NG; ++q) v += red[q * BA * BG + e];
+        const int a = a0 + e / BG, g = g0 + e % BG;
+        if (a < c_a && g < c_g && v != 0.f) atomicAdd(base + (int64_t)a * c_g + g, v);
+      }
+      __syncthreads();
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < TA; ++i) {
       int a = a0 + ta * TA + i;
@@ -265,10 +289,16 @@ __global__ void __launch_bounds__(WG_THREADS)
     __syncthreads();
     for (int p = grp; p < np; p += NG) {
       float a[TA], g[TG];
+      if (TA == 4 && TG == 4) {  // rows are 16-byte aligned (row stride BA + 4 floats): one LDS.128 per operand
+        const float4 av = *(const float4*)&As[p][ta * 4], gv = *(const float4*)&Gs[p][tg * 4];
+        a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+      } else {
 #pragma unroll
-      for (int i = 0; i < TA; ++i) a[i] = As[p][ta * TA + i];
+        for (int i = 0; i < TA; ++i) a[i] = As[p][ta * TA + i];
 #pragma unroll
-      for (int j = 0; j < TG; ++j) g[j] = Gs[p][tg * TG + j];
+        for (int j = 0; j < TG; ++j) g[j] = Gs[p][tg * TG + j];
+      }
 #pragma unroll
       for (int i = 0; i < TA; ++i)
 #pragma unroll

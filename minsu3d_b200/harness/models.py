@@ -374,6 +374,71 @@ class HAIS(GeneralModel):
         return losses
 
 
+def soft_grouping_loop(cfg, semantic_scores, offsets, point_xyz, vert_batch_ids):
+    """softgroup.py:43-86 as written: one ball query + BFS clustering per semantic class (kept as the restatement the
+    batched version below is checked against)."""
+    idx_list, off_list = [], []
+    n_prop, n_pts = 0, 0
+    for class_id in range(cfg.classes):
+        if class_id + 1 in cfg.ignore_classes:
+            continue
+        object_idxs = (semantic_scores[:, class_id] > cfg.sg_score_thr).nonzero().view(-1)
+        if object_idxs.size(0) < cfg.sg_min_npoint:
+            continue
+        batch_idxs_ = vert_batch_ids[object_idxs]
+        batch_offsets_ = torch.cumsum(torch.bincount(batch_idxs_ + 1), dim=0).int()
+        xyz = (point_xyz[object_idxs] + offsets[object_idxs]).contiguous()
+        idx, start_len = common_ops.ballquery_batch_p(xyz, batch_idxs_, batch_offsets_, cfg.sg_radius, cfg.sg_mean_active)
+        p_idx, p_off = softgroup_ops.sg_bfs_cluster(cfg.point_num_avg, idx, start_len, cfg.sg_npoint_thr, class_id)
+        if p_idx.size(0) == 0:
+            continue
+        p_idx = p_idx.long()
+        p_idx[:, 1] = object_idxs[p_idx[:, 1]]
+        p_idx[:, 0] += n_prop
+        idx_list.append(p_idx)
+        off_list.append(p_off[1:] + n_pts if off_list else p_off)
+        n_prop += p_off.numel() - 1
+        n_pts += p_idx.size(0)
+    if not idx_list:
+        return None
+    return torch.cat(idx_list, dim=0), torch.cat(off_list)
+
+
+def soft_grouping(cfg, semantic_scores, offsets, point_xyz, vert_batch_ids):
+    """All classes of softgroup.py:43-86 in one ball query and one clustering pass: the per-class point sets are
+    stacked class by class and every (class, scene) pair gets its own batch index, so neighbour lists never cross
+    classes; cluster_select mode 3 applies the per-class size threshold.  Proposals come out in the reference's
+    order (classes ascending, seeds ascending inside a class).  Two host reads instead of ~4 per class."""
+    n_batch = int(vert_batch_ids.max().item()) + 1 if vert_batch_ids.numel() else 1
+    classes = [c for c in range(cfg.classes) if c + 1 not in cfg.ignore_classes]
+    if not classes or len(classes) * n_batch > 255:  # composite batch index is uint8 like the reference's
+        return soft_grouping_loop(cfg, semantic_scores, offsets, point_xyz, vert_batch_ids)
+    dev = semantic_scores.device
+    cls_t = torch.tensor(classes, device=dev)
+    mask = (semantic_scores[:, cls_t] > cfg.sg_score_thr).t()                 # [n_cls, N]
+    mask = mask & (mask.sum(1, keepdim=True) >= cfg.sg_min_npoint)            # classes below min_npoint are skipped
+    slot, pts = mask.nonzero(as_tuple=True)                                   # class-major, points ascending
+    if pts.numel() == 0:
+        return None
+    class_id = cls_t[slot]
+    batch_idxs_ = (slot * n_batch + vert_batch_ids[pts].long()).to(torch.uint8)
+    batch_offsets_ = torch.cumsum(torch.bincount(batch_idxs_.long() + 1, minlength=len(classes) * n_batch + 1),
+                                  dim=0).int()
+    xyz = (point_xyz[pts] + offsets[pts]).contiguous()
+    idx, start_len = ops.ballquery(xyz, batch_idxs_.contiguous(), batch_offsets_, cfg.sg_radius)
+    mean = torch.tensor(cfg.point_num_avg, dtype=torch.float32, device=dev)
+    thr = torch.full_like(mean, float(cfg.sg_npoint_thr))
+    thr = torch.where(mean != -1, thr * mean, thr)                             # bfs_cluster.cpp:116-121, fp32
+    comp = ops.cluster_label(idx, start_len, None)
+    p_idx, p_off = ops.cluster_extract(idx, start_len, class_id.to(torch.int16).contiguous(), comp, mode=3,
+                                       point_num_avg=thr.contiguous())
+    if p_idx.size(0) == 0:
+        return None
+    p_idx = p_idx.long()
+    p_idx[:, 1] = pts[p_idx[:, 1]]
+    return p_idx, p_off
+
+
 class SoftGroup(GeneralModel):
     """softgroup.py:11-183."""
 
@@ -395,28 +460,8 @@ class SoftGroup(GeneralModel):
         scores, offsets = self._cluster_inputs(data, out)
         semantic_scores = scores.softmax(dim=-1)
         offsets = offsets.detach()
-        idx_list, off_list = [], []
-        n_prop, n_pts = 0, 0
-        for class_id in range(cfg.classes):
-            if class_id + 1 in cfg.ignore_classes:
-                continue
-            object_idxs = (semantic_scores[:, class_id] > cfg.sg_score_thr).nonzero().view(-1)
-            if object_idxs.size(0) < cfg.sg_min_npoint:
-                continue
-            batch_idxs_ = data["vert_batch_ids"][object_idxs]
-            batch_offsets_ = torch.cumsum(torch.bincount(batch_idxs_ + 1), dim=0).int()
-            xyz = (data["point_xyz"][object_idxs] + offsets[object_idxs]).contiguous()
-            idx, start_len = common_ops.ballquery_batch_p(xyz, batch_idxs_, batch_offsets_, cfg.sg_radius, cfg.sg_mean_active)
-            p_idx, p_off = softgroup_ops.sg_bfs_cluster(cfg.point_num_avg, idx, start_len, cfg.sg_npoint_thr, class_id)
-            if p_idx.size(0) == 0:
-                continue
-            p_idx = p_idx.long()
-            p_idx[:, 1] = object_idxs[p_idx[:, 1]]
-            p_idx[:, 0] += n_prop
-            idx_list.append(p_idx)
-            off_list.append(p_off[1:] + n_pts if off_list else p_off)
-            n_prop += p_off.numel() - 1
-            n_pts += p_idx.size(0)
+        proposals = soft_grouping(cfg, semantic_scores, offsets, data["point_xyz"], data["vert_batch_ids"])
+        idx_list, off_list = ([proposals[0]], [proposals[1]]) if proposals is not None else ([], [])
         out["proposals_idx"] = None
         if not idx_list:
             return out

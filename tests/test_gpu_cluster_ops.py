@@ -339,3 +339,27 @@ def test_clusters_voxelize_bit_exact(n_cluster, scale, shape, idx_dtype):
     assert np.array_equal(got.cpu().numpy(), seq.cpu().numpy())
     assert np.array_equal(got.cpu().numpy(), want)
     assert got[:, 1:].min() >= 0 and got[:, 1:].max() < shape + 1
+
+
+def test_soft_grouping_all_classes_in_one_pass_matches_the_per_class_loop():
+    """softgroup.py:43-86: the batched grouping (stacked classes, composite batch index, cluster_select mode 3) returns
+    the proposals of the reference's per-class loop, point for point and in the same order."""
+    from minsu3d_b200.harness import models
+    cfg = models.Config.for_model("softgroup", proposal_source="gt_noise")
+    rng = np.random.default_rng(31)
+    xyz, lab, bidx, offs = clustered_points(rng, 40_000)
+    n = xyz.shape[0]
+    # soft scores: the blob label dominates, a second class often passes the 0.2 threshold as well
+    scores = rng.random((n, cfg.classes)).astype(np.float32) * 0.15
+    scores[np.arange(n), lab % cfg.classes] += 0.6
+    second = (lab + 3) % cfg.classes
+    scores[np.arange(n), second] += (rng.random(n) < 0.5) * 0.3
+    scores /= scores.sum(1, keepdims=True)
+    offsets = (rng.standard_normal((n, 3)) * 0.01).astype(np.float32)
+    args = (cfg, _dev(scores), _dev(offsets), _dev(xyz), _dev(bidx))
+    want = models.soft_grouping_loop(*args)
+    got = models.soft_grouping(*args)
+    assert want is not None and got is not None
+    assert torch.equal(got[1], want[1])
+    assert torch.equal(got[0], want[0])
+    assert want[1].numel() - 1 >= 4  # several proposals, from more than one class

@@ -35,7 +35,7 @@ def main():
     # ---- config 2: HAIS train step, batch 8 scenes per GPU -------------------------------------------
     batch = 8
     pool = [scenes.make_batch([b * batch + s for s in range(batch)], dev, 100_000) for b in range(2)]
-    tr = train.Trainer(models.Config.for_model("hais", proposal_source="gt_noise"), dev)
+    tr = train.Trainer(models.Config.for_model("hais", proposal_source="gt_noise"), dev, reserve_gb=24.0)
     steps = 4
     t = timed(lambda i: tr.step(pool[i % 2]), steps, 4)
     out["hais_train"] = {"scenes_per_s": batch * steps / t, "ms_per_step": t / steps * 1e3, "batch_per_gpu": batch,
