@@ -390,7 +390,7 @@ int conv_wgrad_simt(const float* A, const float* G, const int32_t* src, const in
   int64_t chunks = cdiv(max_pairs, 64) + K;
   if (c_a <= 16 && c_g <= 16) {
     int gx = (int)std::min<int64_t>(chunks, 4 * B2S_SM_COUNT);
-    conv_wgrad_kernel<16, 16, 4, 4, 128><<<dim3(gx, 1, 1), WG_THREADS, 0, stream>>>(A, G, src, dst, k_offsets, gW, K, c_a, c_g);
+    conv_wgrad_kernel<16, 16, 4, 4, 256><<<dim3(gx, 1, 1), WG_THREADS, 0, stream>>>(A, G, src, dst, k_offsets, gW, K, c_a, c_g);
   } else if (c_a <= 32 && c_g <= 32) {
     int gx = (int)std::min<int64_t>(chunks, 4 * B2S_SM_COUNT);
     conv_wgrad_kernel<32, 32, 4, 4, 128><<<dim3(gx, 1, 1), WG_THREADS, 0, stream>>>(A, G, src, dst, k_offsets, gW, K, c_a, c_g);
