@@ -426,7 +426,7 @@ struct GridOrderArgs {
   const int32_t* cluster_offsets;
   const int32_t* seeds;
   int32_t* cluster_idxs;
-  int32_t *cid, *seedcid, *pos, *parent, *F0, *F1, *cnt, *base, *fstart, *fnext, *filled, *blocksum;
+  int32_t *cid, *seedcid, *parent, *F0, *F1, *cnt, *base, *fstart, *filled, *blocksum;
   unsigned* bar;
   int n, n_cluster;
 };
@@ -867,9 +867,9 @@ int b2s_cluster_order(const int32_t* nbr_idx, const int32_t* start_len, const in
   }
   if (n == 0 || n_cluster == 0) return B2S_OK;
   Workspace w(ws, ws_bytes);
-  // measured on the benchmark batch (228k foreground points): device-wide variant 1.2 ms (raw coordinates) /
-  // 3.0 ms (shifted), per-cluster variant 1.7 ms / 9 ms -> the per-cluster kernel is only used for small inputs,
-  // where a cooperative launch of 296 CTAs is all overhead
+  // measured on the benchmark batch (136k foreground points): device-wide variant ~1.0 ms (raw coordinates, deep
+  // sparse graph) / ~0.9 ms (shifted, 55 M edges); the per-cluster variant was 1.7 ms / 9 ms when last compared ->
+  // it is only used for small inputs, where a cooperative launch of 296 CTAs is all overhead
   (void)n_active;
   const bool dense = n >= 8192;
   if (!dense) {
@@ -913,14 +913,12 @@ int b2s_cluster_order(const int32_t* nbr_idx, const int32_t* start_len, const in
   a.bar = w.take<unsigned>(64);
   a.cid = w.take<int32_t>(n);
   a.seedcid = w.take<int32_t>(n);
-  a.pos = w.take<int32_t>(n);
   a.parent = w.take<int32_t>(n);
   a.F0 = w.take<int32_t>(n);
   a.F1 = w.take<int32_t>(n);
   a.cnt = w.take<int32_t>(n + 1);
   a.base = w.take<int32_t>(n + 1);
-  a.fstart = w.take<int32_t>(n + 2);
-  a.fnext = w.take<int32_t>(n + 2);
+  a.fstart = w.take<int32_t>(2 * (n + 2));  // double-buffered per level
   a.filled = w.take<int32_t>(2 * (n + 2));
   a.blocksum = w.take<int32_t>(4096);
   if (!a.blocksum) {
