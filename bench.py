@@ -126,7 +126,9 @@ def dominant_kernel_roofline(data, device):
     hbm, bf16, which = _peaks()
     coords = data["voxel_xyz"]
     table, _, _, oc = ops.coord_unique(coords, 1)
-    nbr, tile_mask = ops.kernel_map(oc, table, 3, 1, with_tile_mask=True)  # what the ME layer passes to every conv
+    nbr, tile_mask = ops.kernel_map(oc, table, 3, 1, with_tile_mask=True)
+    # what the ME layer passes to every tcgen05 conv on a map of this size: the mask-sorted tile schedule
+    row_perm, nbr_sorted, tile_mask_sorted = ops.tile_order(nbr)
     m = oc.size(0)
     pairs = int((nbr >= 0).sum().item())
     cin = cout = 16
@@ -134,22 +136,29 @@ def dominant_kernel_roofline(data, device):
     w = torch.randn(27, cin, cout, device=device) * 0.05
     flush = torch.empty(256 * 1024 * 1024 // 4, device=device)
 
-    def timed(algo):
+    def timed(algo, sorted_tiles=False):
+        def call():
+            if sorted_tiles:
+                return ops.conv_table(x, w, nbr_sorted, m, 27, cin, cout, algo=algo, tile_mask=tile_mask_sorted,
+                                      out_rows=row_perm)
+            return ops.conv_table(x, w, nbr, m, 27, cin, cout, algo=algo, tile_mask=tile_mask)
         for _ in range(3):
-            ops.conv_table(x, w, nbr, m, 27, cin, cout, algo=algo, tile_mask=tile_mask)
+            call()
         times = []
         for _ in range(10):
             flush.zero_()  # L2 flush: 256 MB > 126 MB
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.conv_table(x, w, nbr, m, 27, cin, cout, algo=algo, tile_mask=tile_mask)
+            call()
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1) * 1e-3)
         return float(np.mean(times))
 
-    t = timed(ops.ALGO_TC_3XTF32)
+    t = timed(ops.ALGO_TC_3XTF32, sorted_tiles=True)
+    t_rows = timed(ops.ALGO_TC_3XTF32)
     t_fma = timed(ops.ALGO_SIMT)
+    popc = lambda tm: float(sum(bin(v & 0xFFFFFFFF).count("1") for v in tm.tolist())) / max(tm.numel(), 1)
     # conv fwd bytes = 4*(M_in*Cin + M_out*Cout) + 4*P + 4*K*Cin*Cout ; flops = 2*P*Cin*Cout
     alg_bytes = 4 * (m * cin + m * cout) + 4 * pairs + 4 * 27 * cin * cout
     flops = 2.0 * pairs * cin * cout
@@ -161,12 +170,13 @@ def dominant_kernel_roofline(data, device):
             tj = json.load(f)
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     return {"traffic_source": traffic_src, "kernel": "conv_tc_kernel<false,3> + pack_weights_kernel (tcgen05 3xTF32 implicit GEMM, 3^3 conv 16->16 on the "
-                      "level-0 map of the benchmark batch)",
+                      "level-0 map of the benchmark batch, mask-sorted tiles)",
             "bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": hbm, "unit": "GB/s",
             "frac": alg_bytes / t / 1e9 / hbm, "traffic": traffic, "peak_source": which + " (burst copy)",
             "us_per_launch": t * 1e6, "rows": m, "pairs": pairs, "algorithmic_bytes": alg_bytes,
             "useful_tflops": flops / t / 1e12, "dense_equivalent_tflops": 2.0 * m * 27 * cin * cout * 3 / t / 1e12,
-            "fp32_fma_path_us": t_fma * 1e6,
+            "fp32_fma_path_us": t_fma * 1e6, "row_order_us": t_rows * 1e6,
+            "active_offsets_per_tile": {"mask_sorted": popc(tile_mask_sorted), "row_order": popc(tile_mask)},
             "note": "16-channel layers are gather (L2) bound: ~6 useful FLOP per algorithmic byte; tensor-pipe share is "
                     "reported by ncu in profiles/",
             "timing": "CUDA events on the launch stream, L2 flushed (256 MB write) between launches"}

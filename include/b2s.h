@@ -77,6 +77,17 @@ int b2s_kernel_map(const int32_t* out_coords, int64_t n_out, int32_t ksize, int3
                    const uint64_t* table_keys, const int32_t* table_vals, int64_t cap,
                    int32_t* nbr, uint32_t* tile_mask, b2s_stream_t stream);
 
+/* Mask-sorted tile order of a 3^3 neighbour table (K = 27) for b2s_conv_table_rows: rows are stably sorted by
+ * (which faces of the stencil hold a neighbour, 27-bit neighbour mask) so that the 128-row tiles of the
+ * tcgen05 convolution see few distinct offsets (the row order MinkowskiEngine defines -- first occurrence,
+ * SURVEY appendix A.2 -- mixes floors, walls and edges in every tile).  Purely a schedule: results unchanged.
+ *   row_perm   [n_out] int32: original row of sorted position t
+ *   nbr_sorted [n_out, K] int32: nbr[row_perm[t], :]
+ *   tile_mask  [ceil(n_out/128)] uint32: active-offset masks of the sorted tiles                          */
+size_t b2s_tile_order_ws_bytes(int64_t n_out);
+int b2s_tile_order(const int32_t* nbr, int64_t n_out, int32_t K, int32_t* row_perm, int32_t* nbr_sorted,
+                   uint32_t* tile_mask, void* ws, size_t ws_bytes, b2s_stream_t stream);
+
 /* Canonical per-offset pair lists (sorted by kidx, then by output row) from a neighbour table.
  *   pair_in/pair_out [>= number of pairs] int32, k_offsets [K+1] int32 (CSR over kidx),
  *   d_count int32[1] = total pairs.  Upper bound on pairs: n_out*K.                              */
@@ -108,6 +119,13 @@ int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, const uin
                    float* out, int64_t n_out, int32_t K, int32_t c_in, int32_t c_out,
                    int32_t w_transposed, int32_t k_reversed, int32_t algo,
                    void* ws, size_t ws_bytes, b2s_stream_t stream);
+/* b2s_conv_table over mask-sorted tiles (b2s_tile_order below): row t of the permuted table is stored at
+ * out[out_rows[t], :]; same sum, same k order, fewer all-empty (tile, offset) slabs.  tcgen05 path only
+ * (c_in, c_out multiples of 16, K <= 32; algo 0/2 = 3xTF32, 3 = TF32; algo 1 is rejected).            */
+int b2s_conv_table_rows(const float* A, const float* W, const int32_t* nbr_sorted, const uint32_t* tile_mask,
+                        const int32_t* out_rows, float* out, int64_t n_out, int32_t K, int32_t c_in,
+                        int32_t c_out, int32_t w_transposed, int32_t k_reversed, int32_t algo,
+                        void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_conv_pairs(const float* A, const float* W, const int32_t* src, const int32_t* dst,
                    const int32_t* k_offsets, float* out, int32_t K, int32_t c_in, int32_t c_out,
                    int32_t w_transposed, int64_t max_pairs, int32_t algo,

@@ -25,7 +25,8 @@ class _ConvSame(torch.autograd.Function):
     def forward(ctx, feats, kernel, kmap):
         feats = feats.contiguous()
         K, cin, cout = kernel.shape
-        out = ops.conv_table(feats, kernel, kmap.nbr, kmap.n_out, K, cin, cout, tile_mask=kmap.tile_mask)
+        nbr, tile_mask, out_rows = kmap.table_for(cin, cout)
+        out = ops.conv_table(feats, kernel, nbr, kmap.n_out, K, cin, cout, tile_mask=tile_mask, out_rows=out_rows)
         ctx.save_for_backward(feats, kernel)
         ctx.kmap = kmap
         return out
@@ -39,8 +40,9 @@ class _ConvSame(torch.autograd.Function):
         gin = gk = None
         if ctx.needs_input_grad[0]:
             # nbr[i, K-1-k] = o  <=>  nbr[o, k] = i: reuse the table with reversed, transposed weights
-            gin = ops.conv_table(gout, kernel, kmap.nbr, kmap.n_in, K, cout, cin, w_transposed=True, k_reversed=True,
-                                 tile_mask=kmap.tile_mask)
+            nbr, tile_mask, out_rows = kmap.table_for(cout, cin)
+            gin = ops.conv_table(gout, kernel, nbr, kmap.n_in, K, cout, cin, w_transposed=True, k_reversed=True,
+                                 tile_mask=tile_mask, out_rows=out_rows)
         if ctx.needs_input_grad[1]:
             pin, pout, koff, maxp = kmap.pairs()
             gk = ops.conv_wgrad(feats, gout, pin, pout, koff, K, cin, cout, maxp)

@@ -60,6 +60,23 @@ class KernelMap:
         self.K = nbr.size(1)
         self._pairs = None
         self._exact = exact_pairs
+        self._sorted = None
+
+    # Large 3^3 maps run the tcgen05 convolution over mask-sorted tiles (ops.tile_order): in first-occurrence row
+    # order every 128-row tile sees all 27 offsets, sorted tiles see ~13 on ScanNet-shaped scenes.  The sort costs
+    # about one convolution and is shared by the ~16 forward / data-gradient launches on the map.
+    SORTED_MIN_ROWS = 32768
+
+    def table_for(self, c_in, c_out, algo=None):
+        """(nbr, tile_mask, out_rows) to hand to ops.conv_table for a c_in -> c_out product on this map."""
+        algo = ops.get_conv_algo() if algo is None else algo
+        if (self.K == 27 and self.n_out >= self.SORTED_MIN_ROWS and self.n_in == self.n_out
+                and algo != ops.ALGO_SIMT and ops.conv_tc_shape_ok(self.K, c_in, c_out)):
+            if self._sorted is None:
+                self._sorted = ops.tile_order(self.nbr)
+            row_perm, nbr_sorted, tile_mask = self._sorted
+            return nbr_sorted, tile_mask, row_perm
+        return self.nbr, self.tile_mask, None
 
     def pairs(self):
         """(pair_in, pair_out, k_offsets, max_pairs): sorted by (kernel offset, output row)."""

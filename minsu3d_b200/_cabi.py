@@ -32,6 +32,10 @@ _SIGNATURES = {
     "b2s_pairs_from_nbr": (c_i32, [_P, c_i64, c_i32, c_i64, _P, _P, _P, _P, _P, c_size, _P]),
     "b2s_conv_ws_bytes": (c_size, [c_i32, c_i32, c_i32]),
     "b2s_conv_table": (c_i32, [_P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P, c_size, _P]),
+    "b2s_conv_table_rows": (c_i32, [_P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P, c_size,
+                                    _P]),
+    "b2s_tile_order_ws_bytes": (c_size, [c_i64]),
+    "b2s_tile_order": (c_i32, [_P, c_i64, c_i32, _P, _P, _P, _P, c_size, _P]),
     "b2s_conv_pairs": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, _P, c_size, _P]),
     "b2s_conv_wgrad": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i64, c_i32, _P]),
     "b2s_bn_ws_bytes": (c_size, [c_i64, c_i32]),
@@ -94,7 +98,7 @@ class _Namespace:
 # kernels launched by one call of each entry point (CUB scan = 2, 64-bit radix sort ~ 10);
 # used for the `gpu_launches` figure of bench.py
 KERNELS_PER_CALL = {
-    "b2s_coord_unique": 6, "b2s_kernel_map": 1, "b2s_pairs_from_nbr": 4, "b2s_conv_table": 2, "b2s_conv_pairs": 2,
+    "b2s_coord_unique": 6, "b2s_kernel_map": 1, "b2s_pairs_from_nbr": 4, "b2s_conv_table": 2, "b2s_conv_table_rows": 2, "b2s_tile_order": 7, "b2s_conv_pairs": 2,
     "b2s_conv_wgrad": 1, "b2s_bn_stats": 1, "b2s_bn_forward": 2, "b2s_bn_apply": 1, "b2s_bn_backward": 2, "b2s_gather_rows": 1,
     "b2s_scatter_add_rows": 1, "b2s_ballquery_count": 16, "b2s_ballquery_fill": 2, "b2s_cluster_label": 5,
     "b2s_cluster_select": 7, "b2s_cluster_order": 4, "b2s_cluster_centers": 1, "b2s_ha_assign": 1,

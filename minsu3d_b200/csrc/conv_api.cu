@@ -9,7 +9,7 @@ int conv_wgrad_simt(const float*, const float*, const int32_t*, const int32_t*, 
 bool conv_tc_supported(int K, int c_in, int c_out);
 size_t conv_tc_ws_bytes(int K, int c_in, int c_out);
 int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* dst, const int32_t* k_offsets,
-            const uint32_t* tile_mask,
+            const uint32_t* tile_mask, const int32_t* out_rows,
             float* out, int64_t n_out, int64_t max_pairs, int K, int c_in, int c_out, int wT, int krev, int nsplit,
             bool pairs, void* ws, size_t ws_bytes, cudaStream_t stream);
 }  // namespace b2s
@@ -47,9 +47,26 @@ int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, const uin
   algo = pick(algo, K, c_in, c_out, "conv_table", &nsplit);
   if (algo < 0) return B2S_E_INVALID;
   if (algo >= 2)
-    return conv_tc(A, W, nbr, nullptr, nullptr, tile_mask, out, n_out, 0, K, c_in, c_out, w_transposed, k_reversed,
-                   nsplit, false, ws, ws_bytes, stream);
+    return conv_tc(A, W, nbr, nullptr, nullptr, tile_mask, nullptr, out, n_out, 0, K, c_in, c_out, w_transposed,
+                   k_reversed, nsplit, false, ws, ws_bytes, stream);
   return conv_table_simt(A, W, nbr, out, n_out, K, c_in, c_out, w_transposed, k_reversed, stream);
+}
+
+int b2s_conv_table_rows(const float* A, const float* W, const int32_t* nbr_sorted, const uint32_t* tile_mask,
+                        const int32_t* out_rows, float* out, int64_t n_out, int32_t K, int32_t c_in, int32_t c_out,
+                        int32_t w_transposed, int32_t k_reversed, int32_t algo, void* ws, size_t ws_bytes,
+                        b2s_stream_t stream) {
+  if (n_out < 0 || K < 1 || K > 32 || c_in < 1 || c_out < 1 || !nbr_sorted || !out_rows) {
+    set_error("conv_table_rows: invalid argument");
+    return B2S_E_INVALID;
+  }
+  if (algo == 1 || !conv_tc_supported(K, c_in, c_out)) {
+    set_error("conv_table_rows: only the tcgen05 path takes a row permutation (c_in, c_out multiples of 16)");
+    return B2S_E_INVALID;
+  }
+  const int nsplit = (algo == 3) ? 1 : 3;
+  return conv_tc(A, W, nbr_sorted, nullptr, nullptr, tile_mask, out_rows, out, n_out, 0, K, c_in, c_out, w_transposed,
+                 k_reversed, nsplit, false, ws, ws_bytes, stream);
 }
 
 int b2s_conv_pairs(const float* A, const float* W, const int32_t* src, const int32_t* dst,
@@ -64,7 +81,7 @@ int b2s_conv_pairs(const float* A, const float* W, const int32_t* src, const int
   algo = pick(algo, K, c_in, c_out, "conv_pairs", &nsplit);
   if (algo < 0) return B2S_E_INVALID;
   if (algo >= 2)
-    return conv_tc(A, W, src, dst, k_offsets, nullptr, out, 0, max_pairs, K, c_in, c_out, w_transposed, 0, nsplit, true,
+    return conv_tc(A, W, src, dst, k_offsets, nullptr, nullptr, out, 0, max_pairs, K, c_in, c_out, w_transposed, 0, nsplit, true,
                    ws, ws_bytes, stream);
   return conv_pairs_simt(A, W, src, dst, k_offsets, out, K, c_in, c_out, w_transposed, max_pairs, stream);
 }

@@ -172,7 +172,8 @@ struct TcArgs {
   const int32_t* idx;    // TABLE: nbr [n_out, K] (or NULL = identity, K == 1); PAIRS: src
   const int32_t* dst;    // PAIRS: destination rows
   const int32_t* k_offsets;
-  const uint32_t* tile_mask;  // TABLE, optional: active-offset mask per tile (b2s_kernel_map)
+  const uint32_t* tile_mask;  // TABLE, optional: active-offset mask per tile (b2s_kernel_map / b2s_tile_order)
+  const int32_t* out_rows;    // TABLE, optional: tile row t is stored at out[out_rows[t]] (b2s_tile_order)
   float* out;
   int64_t n_out;
   int64_t bp_half;       // floats in one image
@@ -330,6 +331,11 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
     // trip-count tests: a warp issues in order, so every divergent branch / dependent latency in the per-slab
     // chain directly lengthens the slab period.
     const int r = tid;
+    // mask-sorted tiles (tile_order.cu): the destination row comes from the permutation; loaded here so that
+    // its latency is hidden behind the main loop
+    int64_t orow = -1;
+    int orow_perm = -1;
+    if (!PAIRS && a.out_rows != nullptr && r < rows) orow_perm = __ldg(a.out_rows + row0 + r);
     const float* __restrict__ Ag = a.A;
     const int c_in = a.c_in;
     const int32_t* my_idx = s_idx + (PAIRS ? r : r * K);
@@ -393,8 +399,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
       if (t + 2 < T) store_slab(rc);
     }
     // =========================== epilogue (thread = TMEM lane = tile row) ====================
-    int64_t orow = -1;
-    if (r < rows) orow = PAIRS ? (int64_t)s_idx[TC_BM + r] : row0 + r;
+    if (r < rows) orow = PAIRS ? (int64_t)s_idx[TC_BM + r] : (orow_perm >= 0 ? (int64_t)orow_perm : row0 + r);
     if (T > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -538,7 +543,7 @@ static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream) {
 
 // ws: packed weights, conv_tc_ws_bytes(K, c_in, c_out) bytes
 int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* dst, const int32_t* k_offsets,
-            const uint32_t* tile_mask, float* out, int64_t n_out, int64_t max_pairs, int K, int c_in, int c_out, int wT, int krev, int nsplit,
+            const uint32_t* tile_mask, const int32_t* out_rows, float* out, int64_t n_out, int64_t max_pairs, int K, int c_in, int c_out, int wT, int krev, int nsplit,
             bool pairs, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (ws_bytes < conv_tc_ws_bytes(K, c_in, c_out)) {
     set_error("conv_tc: workspace too small");
@@ -555,6 +560,7 @@ int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* d
   a.dst = dst;
   a.k_offsets = k_offsets;
   a.tile_mask = (!pairs && K <= 32) ? tile_mask : nullptr;
+  a.out_rows = pairs ? nullptr : out_rows;
   a.out = out;
   a.n_out = n_out;
   a.bp_half = half;

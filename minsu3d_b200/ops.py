@@ -103,6 +103,26 @@ def kernel_map(out_coords, table, ksize, dil, with_tile_mask=False):
     return (nbr, tile_mask) if with_tile_mask else nbr
 
 
+def tile_order(nbr):
+    """Mask-sorted tile order of a 3^3 neighbour table: (row_perm[n] i32, nbr_sorted[n,27] i32, tile_mask i32).
+
+    A schedule for conv_table(..., out_rows=row_perm): tiles of 128 sorted rows share their neighbour pattern, so
+    the tcgen05 kernel skips most empty offsets.  Results are unchanged.
+    """
+    require_cuda(nbr)
+    require(nbr.dtype == I32 and nbr.dim() == 2 and nbr.size(1) == 27 and nbr.is_contiguous(),
+            "nbr must be a contiguous int32 [n,27] table")
+    n = nbr.size(0)
+    dev = nbr.device
+    row_perm = _dev_i32(n, dev)
+    nbr_sorted = torch.empty_like(nbr)
+    tile_mask = _dev_i32((n + 127) // 128, dev)
+    ws = workspace(lib().b2s_tile_order_ws_bytes(n), dev)
+    check(lib().b2s_tile_order(ptr(nbr), n, 27, ptr(row_perm), ptr(nbr_sorted), ptr(tile_mask), ptr(ws), ws.numel(),
+                               stream()), "tile_order")
+    return row_perm, nbr_sorted, tile_mask
+
+
 def pairs_from_nbr(nbr, exact=False):
     """Canonical pair lists: (pair_in, pair_out, k_offsets[K+1], d_count[1]) sorted by (k, out row).
 
@@ -156,11 +176,24 @@ def _conv_ws(K, c_in, c_out, device):
     return workspace(nbytes, device)
 
 
-def conv_table(A, W, nbr, n_out, K, c_in, c_out, w_transposed=False, k_reversed=False, algo=None, tile_mask=None):
+def conv_tc_shape_ok(K, c_in, c_out):
+    """Shapes the tcgen05 path takes (conv_tc_supported in csrc/conv_tc.cu)."""
+    return 1 <= K <= 32 and c_in >= 16 and c_in % 16 == 0 and c_out >= 16 and c_out % 16 == 0 and c_out <= 256
+
+
+def conv_table(A, W, nbr, n_out, K, c_in, c_out, w_transposed=False, k_reversed=False, algo=None, tile_mask=None,
+               out_rows=None):
+    """out_rows: nbr / tile_mask are the mask-sorted table of tile_order() and out_rows its row permutation."""
     _f32c(A, "A")
     _f32c(W, "W")
     out = torch.empty((n_out, c_out), dtype=torch.float32, device=A.device)
     ws = _conv_ws(K, c_in, c_out, A.device)
+    if out_rows is not None:
+        check(lib().b2s_conv_table_rows(ptr(A), ptr(W), ptr(nbr), ptr(tile_mask), ptr(out_rows), ptr(out), n_out, K,
+                                        c_in, c_out, int(w_transposed), int(k_reversed),
+                                        _default_algo if algo is None else algo, ptr(ws), ws.numel(), stream()),
+              "conv_table_rows")
+        return out
     check(lib().b2s_conv_table(ptr(A), ptr(W), ptr(nbr), ptr(tile_mask), ptr(out), n_out, K, c_in, c_out, int(w_transposed),
                                int(k_reversed), _default_algo if algo is None else algo, ptr(ws), ws.numel(),
                                stream()), "conv_table")

@@ -263,3 +263,32 @@ def clusters_voxelize(clusters_idx, clusters_offset, coords, scale, spatial_shap
     lib().orc_clusters_voxelize(_p(idx), _p(offs), idx.shape[0], offs.shape[0] - 1, _p(coords),
                                 ctypes.c_float(scale), int(spatial_shape), _p(rand), _p(out))
     return out
+
+
+def tile_order(nbr):
+    """Mask-sorted tile order of a 3^3 neighbour table (numpy restatement of csrc/tile_order.cu; builder-defined
+    schedule, no reference counterpart): stable sort of the rows by
+    key = [faces -x,+x,-y,+y,-z,+z of the stencil that hold a neighbour] << 26 | [27-bit mask without the centre].
+    Returns (row_perm i32 [n], nbr_sorted i32 [n,27], tile_mask u32 [ceil(n/128)])."""
+    nbr = np.ascontiguousarray(nbr, np.int32)
+    n = nbr.shape[0]
+    has = nbr >= 0
+    k = np.arange(27)
+    axes = (k % 3, (k // 3) % 3, k // 9)
+    six = np.zeros(n, np.uint32)
+    bit = 0
+    for a in range(3):
+        for side in (0, 2):
+            six |= has[:, axes[a] == side].any(1).astype(np.uint32) << np.uint32(bit)
+            bit += 1
+    m = (has.astype(np.uint32) << k.astype(np.uint32)[None, :]).sum(1, dtype=np.uint32)
+    m26 = (m & np.uint32(0x1FFF)) | ((m >> np.uint32(14)) << np.uint32(13))
+    key = (six << np.uint32(26)) | m26
+    perm = np.argsort(key, kind="stable").astype(np.int32)
+    nbr_sorted = nbr[perm]
+    tiles = (n + 127) // 128
+    padded = np.zeros((tiles * 128, 27), bool)
+    padded[:n] = nbr_sorted >= 0
+    tile_has = padded.reshape(tiles, 128, 27).any(1)
+    tile_mask = (tile_has.astype(np.uint32) << k.astype(np.uint32)[None, :]).sum(1, dtype=np.uint32)
+    return perm, nbr_sorted, tile_mask
