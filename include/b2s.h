@@ -162,6 +162,40 @@ int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, 
                     void* ws, size_t ws_bytes, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * T3 + T5 host-side fusion -- one MinkUNet residual block per call (minsu3d/model/module/common.py:21-50):
+ *     out = conv3(relu(bn2(conv3(relu(bn1(x)))))) + shortcut(x),  shortcut = x or x @ Wds (1x1 convolution)
+ * Same kernels, order and operands as the single-op entry points above (bit-identical results); the point is
+ * one library call / one autograd node per block: the train step is bound by host launch overhead.
+ * Training-mode BatchNorm only (batch statistics, running statistics updated in place).
+ *   nbr/tile_mask: the block's 3^3 map (b2s_kernel_map); nbr_sorted/tile_mask_sorted/row_perm: optional
+ *   b2s_tile_order schedule (all NULL = first-occurrence order).
+ *   forward saves y1 = relu(bn1(x)) [n,c_in], z1 = conv(y1) [n,c_out], y2 = relu(bn2(z1)) [n,c_out],
+ *   stats1 [2,c_in] / stats2 [2,c_out] = (mean, rstd); tmp [n,c_out] is scratch for the 1x1 shortcut (Wds != NULL).
+ *   backward: pair lists of the same map (b2s_pairs_from_nbr) for the weight gradients; ident [n] = 0..n-1 and
+ *   ident_koff = {0, n} drive the 1x1 weight gradient; dgb1 [2,c_in] / dgb2 [2,c_out] = (dgamma, dbeta);
+ *   tmp_a, tmp_b [n,c_out] and tmp_c [n,c_in] are scratch.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b2s_resblock_ws_bytes(int32_t K, int32_t c_in, int32_t c_out);
+int b2s_resblock_forward(const float* x, int64_t n, int32_t c_in, int32_t c_out,
+                         const float* gamma1, const float* beta1, float* rmean1, float* rvar1, const float* W1,
+                         const float* gamma2, const float* beta2, float* rmean2, float* rvar2, const float* W2,
+                         const float* Wds, float eps1, float mom1, float eps2, float mom2,
+                         const int32_t* nbr, const uint32_t* tile_mask, const int32_t* nbr_sorted,
+                         const uint32_t* tile_mask_sorted, const int32_t* row_perm, int32_t K,
+                         float* y1, float* stats1, float* z1, float* y2, float* stats2, float* out, float* tmp,
+                         int32_t* bn_counter, int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream);
+int b2s_resblock_backward(const float* gout, const float* x, const float* y1, const float* z1, const float* y2,
+                          const float* stats1, const float* stats2, const float* gamma1, const float* gamma2,
+                          const float* W1, const float* W2, const float* Wds, int64_t n, int32_t c_in, int32_t c_out,
+                          const int32_t* nbr, const uint32_t* tile_mask, const int32_t* nbr_sorted,
+                          const uint32_t* tile_mask_sorted, const int32_t* row_perm, int32_t K,
+                          const int32_t* pair_in, const int32_t* pair_out, const int32_t* k_offsets, int64_t max_pairs,
+                          const int32_t* ident, const int32_t* ident_koff,
+                          float* gx, float* gW1, float* gW2, float* gWds, float* dgb1, float* dgb2,
+                          float* tmp_a, float* tmp_b, float* tmp_c,
+                          int32_t* bn_counter, int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * V2 -- devoxelise gather and its scatter-add gradient (backbone.py:40, pointgroup.py:88).
  * idx is int64 (voxel_point_map dtype, data_module.py:65).
  * ---------------------------------------------------------------------------------------------- */

@@ -404,3 +404,107 @@ def cat(*sparse_tensors):
     for s in sparse_tensors[1:]:
         first._check_same_map(s)
     return first._like(torch.cat([s.F for s in sparse_tensors], dim=1))
+
+
+# ------------------------------------------------------------------------------------------
+# host-side fusion: one residual block = one autograd node + one library call (csrc/fused.cu)
+# ------------------------------------------------------------------------------------------
+class _ResBlockFn(torch.autograd.Function):
+    """out = conv3(relu(bn2(conv3(relu(bn1(x)))))) + shortcut(x) in training mode; bit-identical to the
+    module-by-module path (same kernels in the same order), but 1 node / 1 call instead of 5-6 each."""
+
+    @staticmethod
+    def forward(ctx, x, g1, b1, w1, g2, b2, w2, wds, bn1, bn2, kmap):
+        x = x.contiguous()
+        n, cin = x.shape
+        cout = w1.size(2)
+        K = w1.size(0)
+        dev = x.device
+        # one buffer for everything the backward needs: y1 [n,cin] | z1 [n,cout] | y2 [n,cout] | stats1 | stats2
+        saved = torch.empty(n * (cin + 2 * cout) + 2 * cin + 2 * cout, dtype=torch.float32, device=dev)
+        out = torch.empty((n, cout), dtype=torch.float32, device=dev)
+        tmp = torch.empty((n, cout), dtype=torch.float32, device=dev) if wds is not None else None
+        base = saved.data_ptr()
+        p_y1, p_z1 = base, base + 4 * n * cin
+        p_y2 = p_z1 + 4 * n * cout
+        p_s1 = p_y2 + 4 * n * cout
+        p_s2 = p_s1 + 8 * cin
+        nbr_s, mask_s, perm = kmap.sorted_tables(cin, cout)
+        algo = ops.get_conv_algo()
+        ws = ops.workspace(ops.resblock_ws_bytes(K, cin, cout), dev)
+        ops.check(ops.lib().b2s_resblock_forward(
+            x.data_ptr(), n, cin, cout,
+            g1.data_ptr(), b1.data_ptr(), ops.ptr(bn1.running_mean), ops.ptr(bn1.running_var), w1.data_ptr(),
+            g2.data_ptr(), b2.data_ptr(), ops.ptr(bn2.running_mean), ops.ptr(bn2.running_var), w2.data_ptr(),
+            ops.ptr(wds), bn1.eps, bn1.momentum if bn1.running_mean is not None else 0.0,
+            bn2.eps, bn2.momentum if bn2.running_mean is not None else 0.0,
+            kmap.nbr.data_ptr(), ops.ptr(kmap.tile_mask), ops.ptr(nbr_s), ops.ptr(mask_s), ops.ptr(perm), K,
+            p_y1, p_s1, p_z1, p_y2, p_s2, out.data_ptr(), ops.ptr(tmp),
+            ops.bn_counter(dev).data_ptr(), algo, ws.data_ptr(), ws.numel(), ops.stream()), "resblock_forward")
+        ctx.save_for_backward(x, saved, g1, g2, w1, w2, wds)
+        ctx.kmap = kmap
+        ctx.algo = algo
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, saved, g1, g2, w1, w2, wds = ctx.saved_tensors
+        kmap = ctx.kmap
+        gout = gout.contiguous()
+        n, cin = x.shape
+        K, _, cout = w1.shape
+        dev = x.device
+        base = saved.data_ptr()
+        p_y1, p_z1 = base, base + 4 * n * cin
+        p_y2 = p_z1 + 4 * n * cout
+        p_s1 = p_y2 + 4 * n * cout
+        p_s2 = p_s1 + 8 * cin
+        gx = torch.empty_like(x)
+        gw1 = torch.empty_like(w1)
+        gw2 = torch.empty_like(w2)
+        gwds = torch.empty_like(wds) if wds is not None else None
+        dgb1 = torch.empty((2, cin), dtype=torch.float32, device=dev)
+        dgb2 = torch.empty((2, cout), dtype=torch.float32, device=dev)
+        scratch = torch.empty(n * (2 * cout + cin), dtype=torch.float32, device=dev)
+        p_a = scratch.data_ptr()
+        p_b = p_a + 4 * n * cout
+        p_c = p_b + 4 * n * cout
+        pin, pout, koff, maxp = kmap.pairs()
+        ident = ident_koff = None
+        if wds is not None:
+            ident, ident_koff = _identity_pairs(n, dev)
+        nbr_s, mask_s, perm = kmap.sorted_tables(cin, cout)
+        ws = ops.workspace(ops.resblock_ws_bytes(K, cin, cout), dev)
+        ops.check(ops.lib().b2s_resblock_backward(
+            gout.data_ptr(), x.data_ptr(), p_y1, p_z1, p_y2, p_s1, p_s2, g1.data_ptr(), g2.data_ptr(),
+            w1.data_ptr(), w2.data_ptr(), ops.ptr(wds), n, cin, cout,
+            kmap.nbr.data_ptr(), ops.ptr(kmap.tile_mask), ops.ptr(nbr_s), ops.ptr(mask_s), ops.ptr(perm), K,
+            pin.data_ptr(), pout.data_ptr(), koff.data_ptr(), int(maxp), ops.ptr(ident), ops.ptr(ident_koff),
+            gx.data_ptr(), gw1.data_ptr(), gw2.data_ptr(), ops.ptr(gwds), dgb1.data_ptr(), dgb2.data_ptr(),
+            p_a, p_b, p_c, ops.bn_counter(dev).data_ptr(), ctx.algo, ws.data_ptr(), ws.numel(), ops.stream()),
+            "resblock_backward")
+        return gx, dgb1[0], dgb1[1], gw1, dgb2[0], dgb2[1], gw2, gwds, None, None, None
+
+
+def residual_block_fusable(x, bn1, conv1, bn2, conv2, downsample):
+    """Training-mode pre-activation residual block on one coordinate map with 3^3 stride-1 convolutions."""
+    b1, b2 = bn1.bn, bn2.bn
+    return (b1.training and b2.training and b1.affine and b2.affine and b1.track_running_stats
+            and b2.track_running_stats and b1.momentum is not None and b2.momentum is not None
+            and conv1.kernel_size == 3 and conv2.kernel_size == 3 and conv1.stride == 1 and conv2.stride == 1
+            and conv1.bias is None and conv2.bias is None and not conv1.is_transpose and not conv2.is_transpose
+            and conv1.in_channels % 4 == 0 and conv1.out_channels % 4 == 0
+            and (downsample is None or (downsample.use_mm and downsample.bias is None))
+            and x.F.is_cuda and x.F.size(0) > 0 and torch.is_grad_enabled())
+
+
+def fused_residual_block(x, bn1, conv1, bn2, conv2, downsample=None):
+    """common.py:21-50 as one call.  bn1/bn2: MinkowskiBatchNorm, conv1/conv2: MinkowskiConvolution(k=3),
+    downsample: MinkowskiConvolution(k=1) or None.  Caller checks residual_block_fusable()."""
+    mgr, key = x.coordinate_manager, x.coordinate_map_key
+    kmap = mgr.kernel_map(key, key, 3)
+    b1, b2 = bn1.bn, bn2.bn
+    torch._foreach_add_([b1.num_batches_tracked, b2.num_batches_tracked], 1)
+    out = _ResBlockFn.apply(x.F, b1.weight, b1.bias, conv1.kernel, b2.weight, b2.bias, conv2.kernel,
+                            None if downsample is None else downsample.kernel, b1, b2, kmap)
+    return SparseTensor(out, coordinate_map_key=key, coordinate_manager=mgr)

@@ -67,6 +67,11 @@ class KernelMap:
     # about one convolution and is shared by the ~16 forward / data-gradient launches on the map.
     SORTED_MIN_ROWS = 32768
 
+    def sorted_tables(self, c_in, c_out, algo=None):
+        """(nbr_sorted, tile_mask_sorted, row_perm) when the sorted schedule applies to this map, else Nones."""
+        nbr, tile_mask, out_rows = self.table_for(c_in, c_out, algo)
+        return (nbr, tile_mask, out_rows) if out_rows is not None else (None, None, None)
+
     def table_for(self, c_in, c_out, algo=None):
         """(nbr, tile_mask, out_rows) to hand to ops.conv_table for a c_in -> c_out product on this map."""
         algo = ops.get_conv_algo() if algo is None else algo

@@ -1,0 +1,154 @@
+// Host-side fusion of the MinkUNet residual block (minsu3d/model/module/common.py:21-50):
+//
+//     out = conv3(relu(bn2(conv3(relu(bn1(x)))))) + shortcut(x),   shortcut = identity | 1x1 convolution
+//
+// The kernels are the ones behind the single-op entry points (bn.cu, conv_tc.cu, conv_simt.cu); what is fused is
+// the HOST side: the PointGroup train step is bound by the ~28 ms the host needs to enqueue ~1000 launches through
+// Python (profiles/r01_host_profile.txt: 171 autograd nodes + 485 library calls per step), and the 32 residual
+// blocks of the two U-Nets account for most of them.  One call here enqueues the 9-11 launches of a block's
+// forward (10-14 of its backward), so a block costs one autograd node and one library call instead of 5-6 each.
+// Results are bit-identical to the op-by-op path: same kernels, same order, same operands.
+#include "common.cuh"
+
+namespace b2s {
+
+__global__ void __launch_bounds__(256)
+    add_inplace_kernel(float4* __restrict__ y, const float4* __restrict__ s, int64_t total4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  float4 a = y[i];
+  const float4 b = __ldg(s + i);
+  a.x += b.x;
+  a.y += b.y;
+  a.z += b.z;
+  a.w += b.w;
+  y[i] = a;
+}
+
+static int add_inplace(float* y, const float* s, int64_t n, int c, cudaStream_t stream) {
+  const int64_t total4 = n * (c / 4);
+  if (total4 == 0) return B2S_OK;
+  add_inplace_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, stream>>>((float4*)y, (const float4*)s, total4);
+  return check_launch("resblock add");
+}
+
+bool conv_tc_supported(int K, int c_in, int c_out);
+
+struct Tables {
+  const int32_t* nbr;
+  const uint32_t* tile_mask;
+  const int32_t* nbr_sorted;  // optional mask-sorted schedule (b2s_tile_order), used by the tcgen05 path
+  const uint32_t* tile_mask_sorted;
+  const int32_t* row_perm;
+  int K;
+};
+
+// stride-1 3^3 product on the block's map: sorted tiles when the caller built them and the tcgen05 path applies
+static int conv_same(const float* A, const float* W, float* out, int64_t n, int c_in, int c_out, int wT, int krev,
+                     int algo, const Tables& t, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (t.nbr_sorted != nullptr && algo != 1 && conv_tc_supported(t.K, c_in, c_out))
+    return b2s_conv_table_rows(A, W, t.nbr_sorted, t.tile_mask_sorted, t.row_perm, out, n, t.K, c_in, c_out, wT, krev,
+                               algo, ws, ws_bytes, stream);
+  return b2s_conv_table(A, W, t.nbr, t.tile_mask, out, n, t.K, c_in, c_out, wT, krev, algo, ws, ws_bytes, stream);
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+#define B2S_TRY(expr)      \
+  do {                     \
+    int rc_ = (expr);      \
+    if (rc_) return rc_;   \
+  } while (0)
+
+extern "C" {
+
+size_t b2s_resblock_ws_bytes(int32_t K, int32_t c_in, int32_t c_out) {
+  const int c = c_in > c_out ? c_in : c_out;
+  return align_up(b2s_bn_ws_bytes(0, c)) + align_up(b2s_conv_ws_bytes(K, c, c)) + 1024;
+}
+
+int b2s_resblock_forward(const float* x, int64_t n, int32_t c_in, int32_t c_out,
+                         const float* gamma1, const float* beta1, float* rmean1, float* rvar1, const float* W1,
+                         const float* gamma2, const float* beta2, float* rmean2, float* rvar2, const float* W2,
+                         const float* Wds, float eps1, float mom1, float eps2, float mom2,
+                         const int32_t* nbr, const uint32_t* tile_mask, const int32_t* nbr_sorted,
+                         const uint32_t* tile_mask_sorted, const int32_t* row_perm, int32_t K,
+                         float* y1, float* stats1, float* z1, float* y2, float* stats2, float* out, float* tmp,
+                         int32_t* bn_counter, int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream) {
+  if (n < 0 || c_in < 4 || c_out < 4 || (c_in & 3) || (c_out & 3) || !nbr || (Wds != nullptr && tmp == nullptr) ||
+      (Wds == nullptr && c_in != c_out)) {
+    set_error("resblock_forward: invalid argument");
+    return B2S_E_INVALID;
+  }
+  if (n == 0) return B2S_OK;
+  Workspace w(ws, ws_bytes);
+  const size_t bn_bytes = b2s_bn_ws_bytes(n, c_in > c_out ? c_in : c_out);
+  char* bn_ws = w.take<char>(bn_bytes);
+  const size_t conv_bytes = ws_bytes > w.off ? ws_bytes - w.off : 0;
+  char* conv_ws = (char*)ws + w.off;
+  if (!bn_ws) {
+    set_error("resblock_forward: workspace too small");
+    return B2S_E_WORKSPACE;
+  }
+  const Tables t{nbr, tile_mask, nbr_sorted, tile_mask_sorted, row_perm, K};
+  // shortcut first (common.py:45), into tmp when it is a 1x1 convolution
+  if (Wds != nullptr)
+    B2S_TRY(b2s_conv_table(x, Wds, nullptr, nullptr, tmp, n, 1, c_in, c_out, 0, 0, algo, conv_ws, conv_bytes, stream));
+  B2S_TRY(b2s_bn_forward(x, n, c_in, eps1, mom1, rmean1, rvar1, gamma1, beta1, 1, y1, stats1, stats1 + c_in, bn_counter,
+                         bn_ws, bn_bytes, stream));
+  B2S_TRY(conv_same(y1, W1, z1, n, c_in, c_out, 0, 0, algo, t, conv_ws, conv_bytes, stream));
+  B2S_TRY(b2s_bn_forward(z1, n, c_out, eps2, mom2, rmean2, rvar2, gamma2, beta2, 1, y2, stats2, stats2 + c_out,
+                         bn_counter, bn_ws, bn_bytes, stream));
+  B2S_TRY(conv_same(y2, W2, out, n, c_out, c_out, 0, 0, algo, t, conv_ws, conv_bytes, stream));
+  return add_inplace(out, Wds != nullptr ? tmp : x, n, c_out, stream);
+}
+
+int b2s_resblock_backward(const float* gout, const float* x, const float* y1, const float* z1, const float* y2,
+                          const float* stats1, const float* stats2, const float* gamma1, const float* gamma2,
+                          const float* W1, const float* W2, const float* Wds, int64_t n, int32_t c_in, int32_t c_out,
+                          const int32_t* nbr, const uint32_t* tile_mask, const int32_t* nbr_sorted,
+                          const uint32_t* tile_mask_sorted, const int32_t* row_perm, int32_t K,
+                          const int32_t* pair_in, const int32_t* pair_out, const int32_t* k_offsets, int64_t max_pairs,
+                          const int32_t* ident, const int32_t* ident_koff,
+                          float* gx, float* gW1, float* gW2, float* gWds, float* dgb1, float* dgb2,
+                          float* tmp_a, float* tmp_b, float* tmp_c,
+                          int32_t* bn_counter, int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream) {
+  if (n < 0 || c_in < 4 || c_out < 4 || (c_in & 3) || (c_out & 3) || !nbr || !pair_in || !pair_out || !k_offsets ||
+      (Wds != nullptr && (!gWds || !ident || !ident_koff)) || (Wds == nullptr && c_in != c_out)) {
+    set_error("resblock_backward: invalid argument");
+    return B2S_E_INVALID;
+  }
+  Workspace w(ws, ws_bytes);
+  const size_t bn_bytes = b2s_bn_ws_bytes(n, c_in > c_out ? c_in : c_out);
+  char* bn_ws = w.take<char>(bn_bytes);
+  const size_t conv_bytes = ws_bytes > w.off ? ws_bytes - w.off : 0;
+  char* conv_ws = (char*)ws + w.off;
+  if (!bn_ws) {
+    set_error("resblock_backward: workspace too small");
+    return B2S_E_WORKSPACE;
+  }
+  const Tables t{nbr, tile_mask, nbr_sorted, tile_mask_sorted, row_perm, K};
+  // second convolution: data gradient (symmetric map: reversed offsets, transposed weights) and weight gradient
+  B2S_TRY(conv_same(gout, W2, tmp_a, n, c_out, c_out, 1, 1, algo, t, conv_ws, conv_bytes, stream));
+  B2S_TRY(b2s_conv_wgrad(y2, gout, pair_in, pair_out, k_offsets, gW2, K, c_out, c_out, max_pairs, algo, stream));
+  // bn2 + relu
+  B2S_TRY(b2s_bn_backward(z1, y2, tmp_a, n, c_out, stats2, stats2 + c_out, gamma2, 1, 1, tmp_b, dgb2, dgb2 + c_out,
+                          bn_counter, bn_ws, bn_bytes, stream));
+  // first convolution
+  B2S_TRY(conv_same(tmp_b, W1, tmp_c, n, c_out, c_in, 1, 1, algo, t, conv_ws, conv_bytes, stream));
+  B2S_TRY(b2s_conv_wgrad(y1, tmp_b, pair_in, pair_out, k_offsets, gW1, K, c_in, c_out, max_pairs, algo, stream));
+  // bn1 + relu
+  B2S_TRY(b2s_bn_backward(x, y1, tmp_c, n, c_in, stats1, stats1 + c_in, gamma1, 1, 1, gx, dgb1, dgb1 + c_in, bn_counter,
+                          bn_ws, bn_bytes, stream));
+  // shortcut
+  if (Wds != nullptr) {
+    B2S_TRY(b2s_conv_table(gout, Wds, nullptr, nullptr, tmp_c, n, 1, c_out, c_in, 1, 0, algo, conv_ws, conv_bytes, stream));
+    B2S_TRY(add_inplace(gx, tmp_c, n, c_in, stream));
+    return b2s_conv_wgrad(x, gout, ident, ident, ident_koff, gWds, 1, c_in, c_out, n, algo, stream);
+  }
+  return add_inplace(gx, gout, n, c_in, stream);
+}
+
+}  // extern "C"

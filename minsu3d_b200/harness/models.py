@@ -17,6 +17,7 @@ import torch.nn.functional as F
 
 from .. import MinkowskiEngine as ME
 from .. import ops
+from ..MinkowskiEngine import modules as me_modules
 from ..common_ops.functions import common_ops, hais_ops, pointgroup_ops, softgroup_ops
 from . import scenes
 
@@ -24,6 +25,9 @@ from . import scenes
 # ------------------------------------------------------------------------------------------
 # MinkUNet pieces (common.py:21-95, backbone.py:8-43, tiny_unet.py:7-19)
 # ------------------------------------------------------------------------------------------
+FUSED_BLOCKS = True  # training-mode residual blocks through b2s_resblock_forward/backward (host-side fusion)
+
+
 class ResidualBlock(nn.Module):
     def __init__(self, in_channels, out_channels, dimension=3, norm_fn=None):
         super().__init__()
@@ -39,6 +43,14 @@ class ResidualBlock(nn.Module):
             ME.MinkowskiConvolution(out_channels, out_channels, kernel_size=3, dimension=dimension))
 
     def forward(self, x):
+        if FUSED_BLOCKS:
+            # one autograd node + one library call for the whole block (csrc/fused.cu); bit-identical to the
+            # module-by-module path below, which stays the reference-shaped fallback (eval mode, odd shapes)
+            br = self.conv_branch
+            ds = None if self.downsample is None else self.downsample[0]
+            if (isinstance(br[0], ME.MinkowskiBatchNorm) and isinstance(br[3], ME.MinkowskiBatchNorm)
+                    and me_modules.residual_block_fusable(x, br[0], br[2], br[3], br[5], ds)):
+                return me_modules.fused_residual_block(x, br[0], br[2], br[3], br[5], ds)
         shortcut = x if self.downsample is None else self.downsample(x)
         y = self.conv_branch(x)
         y += shortcut

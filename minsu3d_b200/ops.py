@@ -228,6 +228,21 @@ def conv_wgrad(A, G, src, dst, k_offsets, K, c_a, c_g, max_pairs, algo=None):
 _BN_COUNTERS = {}
 
 
+_RESBLOCK_WS = {}
+
+
+def resblock_ws_bytes(K, c_in, c_out):
+    key = (K, c_in, c_out)
+    v = _RESBLOCK_WS.get(key)
+    if v is None:
+        v = _RESBLOCK_WS[key] = lib().b2s_resblock_ws_bytes(K, c_in, c_out)
+    return v
+
+
+def bn_counter(device):
+    return _bn_counter(device)
+
+
 def _bn_counter(device):
     """Per-(device, stream) int32 that is zero between launches (last-block-done second stage)."""
     key = (device.index, stream())

@@ -165,3 +165,56 @@ def test_reference_wrappers_run_unmodified_on_dropin(batch):
     q = ME.utils.sparse_quantize(batch["voxel_xyz"].long(), batch["voxel_features"], return_index=True,
                                  return_inverse=True, device="cuda")
     assert q[2].dtype == torch.int64 and torch.equal(q[3], torch.arange(st.F.shape[0], device="cuda"))
+
+
+@pytest.mark.parametrize("cin,cout,n_rows", [(16, 16, 12_000), (32, 16, 12_000), (48, 48, 3_000), (16, 16, 40_000)])
+def test_fused_residual_block_equals_module_by_module(batch, monkeypatch, cin, cout, n_rows):
+    """b2s_resblock_forward/backward (one call per block) vs the MinkowskiEngine-shaped module sequence:
+    identical features, input gradients, BatchNorm gradients and running statistics; weight gradients to 1e-5
+    (their atomic flush order varies run to run).  40k rows also crosses KernelMap.SORTED_MIN_ROWS."""
+    from minsu3d_b200 import MinkowskiEngine as ME
+    from minsu3d_b200.harness import models
+    coords = batch["voxel_xyz"][:n_rows].contiguous()
+    n = coords.size(0)
+    torch.manual_seed(cin * 100 + cout)
+    x0 = torch.randn(n, cin, device="cuda")
+    g = torch.randn(n, cout, device="cuda")
+    blk = models.ResidualBlock(cin, cout, 3).cuda().train()
+    state = {k: v.clone() for k, v in blk.state_dict().items()}
+    res = []
+    for fused in (False, True):
+        monkeypatch.setattr(models, "FUSED_BLOCKS", fused)
+        blk.load_state_dict(state)
+        blk.zero_grad(set_to_none=True)
+        xa = x0.clone().requires_grad_(True)
+        st = ME.SparseTensor(features=xa, coordinates=coords)
+        y = blk(st)
+        assert y.coordinate_map_key == st.coordinate_map_key
+        y.F.backward(g)
+        res.append((y.F.detach().clone(), xa.grad.clone(), {k: p.grad.clone() for k, p in blk.named_parameters()},
+                    {k: v.clone() for k, v in blk.state_dict().items()}))
+    (ya, gxa, ga, sa), (yb, gxb, gb, sb) = res
+    assert torch.equal(ya, yb)
+    assert torch.equal(gxa, gxb)
+    for k in ga:
+        if k.endswith("kernel"):
+            assert _rel(gb[k].cpu().numpy(), ga[k].cpu().numpy()) < 1e-5, k
+        else:
+            assert torch.equal(ga[k], gb[k]), k
+    for k in sa:
+        if not k.endswith("kernel"):
+            assert torch.equal(sa[k], sb[k]), k  # running_mean / running_var / num_batches_tracked
+
+
+def test_fused_blocks_fall_back_in_eval_mode(batch, monkeypatch):
+    from minsu3d_b200 import MinkowskiEngine as ME
+    from minsu3d_b200.harness import models
+    coords = batch["voxel_xyz"][:5000].contiguous()
+    x = torch.randn(coords.size(0), 16, device="cuda")
+    blk = models.ResidualBlock(16, 16, 3).cuda().eval()
+    outs = []
+    for fused in (False, True):
+        monkeypatch.setattr(models, "FUSED_BLOCKS", fused)
+        with torch.no_grad():
+            outs.append(blk(ME.SparseTensor(features=x, coordinates=coords)).F)
+    assert torch.equal(outs[0], outs[1])
