@@ -66,7 +66,13 @@ extern "C" {
 
 size_t b2s_resblock_ws_bytes(int32_t K, int32_t c_in, int32_t c_out) {
   const int c = c_in > c_out ? c_in : c_out;
-  return align_up(b2s_bn_ws_bytes(0, c)) + align_up(b2s_conv_ws_bytes(K, c, c)) + 1024;
+  size_t conv = 0;
+  const int shapes[5][3] = {{K, c_in, c_out}, {K, c_out, c_out}, {K, c_out, c_in}, {1, c_in, c_out}, {1, c_out, c_in}};
+  for (const auto& s : shapes) {
+    const size_t b = b2s_conv_ws_bytes(s[0], s[1], s[2]);
+    conv = b > conv ? b : conv;
+  }
+  return align_up(b2s_bn_ws_bytes(0, c)) + align_up(conv) + 1024;
 }
 
 int b2s_resblock_forward(const float* x, int64_t n, int32_t c_in, int32_t c_out,
