@@ -255,7 +255,9 @@ def run_own(args):
                                       "random-init weights yield proposals; network outputs still get their losses)",
                    "parallelism": "dp%d (scene-sharded, bucketed NCCL gradient all-reduce)" % world,
                    "cache": "per-step working set (activations, ~GBs) >> 126 MB L2; %d batches rotated" % n_pool,
-                   "conv_algo": "tcgen05 3xTF32 implicit GEMM (fp32-class accuracy); fp32 FMA for the 6-channel input conv "
+                   "sizes": "level row counts and uniqueness of the voxel grid come with the batch from the loader (by-product of "
+                               "voxelisation) and are validated on the device every step; no host read of device counts in the "
+                               "backbone", "conv_algo": "tcgen05 3xTF32 implicit GEMM (fp32-class accuracy); fp32 FMA for the 6-channel input conv "
                                 "and the weight gradient"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},

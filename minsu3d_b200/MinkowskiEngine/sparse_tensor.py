@@ -98,11 +98,12 @@ class CoordinateManager:
         self.device = device
         self._maps = {}
         self._kmaps = {}
+        self._size_hints = None  # {tensor stride: rows} reported by the voxeliser (see SparseTensor(level_sizes=...))
 
     # -- maps ---------------------------------------------------------------------------------
-    def insert_and_map(self, coordinates, tensor_stride=1):
+    def insert_and_map(self, coordinates, tensor_stride=1, assume_unique=False):
         """Register coordinates; returns (key, unique_index i32, inverse_mapping i32)."""
-        table, unique_idx, inverse, out_coords = ops.coord_unique(coordinates, quant=1)
+        table, unique_idx, inverse, out_coords = ops.coord_unique(coordinates, quant=1, assume_unique=assume_unique)
         key = CoordinateMapKey(tensor_stride)
         self._maps[key] = _CoordMap(out_coords, table, int(tensor_stride))
         self.device = coordinates.device
@@ -130,10 +131,20 @@ class CoordinateManager:
             if int(stride) == 2 and src.size >= self.PYRAMID_MIN_ROWS:
                 levels = self.PYRAMID_LEVELS
             if levels > 1:
-                for s, table, oc in ops.coord_pyramid(src.coords, in_key.stride, levels):
+                hints = None
+                if self._size_hints is not None:
+                    want = [in_key.stride * 2 ** (i + 1) for i in range(levels)]
+                    if all(w in self._size_hints for w in want):
+                        hints = [self._size_hints[w] for w in want]
+                for s, table, oc in ops.coord_pyramid(src.coords, in_key.stride, levels, size_hints=hints):
                     key = CoordinateMapKey(s)
                     if key not in self._maps:
                         self._maps[key] = _CoordMap(oc, table, s)
+            elif self._size_hints is not None and new_stride in self._size_hints:
+                m = self._size_hints[new_stride]
+                table, _, _, out_coords, d_count = ops.coord_unique_async(src.coords, new_stride)
+                ops.defer_count_check(d_count, m, "coordinate map of tensor stride %d (size hint)" % new_stride)
+                self._maps[out_key] = _CoordMap(out_coords[:m], table, new_stride)
             else:
                 table, _, _, out_coords = ops.coord_unique(src.coords, quant=new_stride)
                 self._maps[out_key] = _CoordMap(out_coords, table, new_stride)
@@ -163,7 +174,13 @@ class SparseTensor:
     """Sparse tensor = features [M, C] float32 + a coordinate map key inside a manager."""
 
     def __init__(self, features, coordinates=None, tensor_stride=1, coordinate_map_key=None,
-                 coordinate_manager=None, quantization_mode=None, device=None, **_unused):
+                 coordinate_manager=None, quantization_mode=None, device=None, coordinates_unique=False,
+                 level_sizes=None, **_unused):
+        """coordinates_unique / level_sizes are extensions (not in MinkowskiEngine): the caller states that the
+        rows are already unique (they come out of sparse_quantize) and, optionally, how many rows the strided
+        maps {tensor stride: rows} will have (the voxeliser knows).  Both remove host reads of device counts, so
+        the host keeps enqueuing while the GPU is still busy; the statements are validated on the device and a
+        wrong one raises at the next host read (ops.run_deferred_checks)."""
         if device is not None:
             features = features.to(device)
         self.quantization_mode = quantization_mode
@@ -185,7 +202,10 @@ class SparseTensor:
                 raise ValueError("coordinates and features have different numbers of rows")
             if coordinate_manager is None:
                 coordinate_manager = CoordinateManager(D=coordinates.size(1) - 1, device=features.device)
-            coordinate_map_key, unique_idx, inverse = coordinate_manager.insert_and_map(coordinates, tensor_stride)
+            if level_sizes is not None:
+                coordinate_manager._size_hints = {int(k): int(v) for k, v in dict(level_sizes).items()}
+            coordinate_map_key, unique_idx, inverse = coordinate_manager.insert_and_map(
+                coordinates, tensor_stride, assume_unique=bool(coordinates_unique))
             self.inverse_mapping = inverse
             self.unique_index = unique_idx
             if unique_idx.numel() != coordinates.size(0):

@@ -25,6 +25,7 @@ from . import scenes
 # ------------------------------------------------------------------------------------------
 # MinkUNet pieces (common.py:21-95, backbone.py:8-43, tiny_unet.py:7-19)
 # ------------------------------------------------------------------------------------------
+ASYNC_SIZES = True   # use the loader's level sizes / uniqueness guarantees instead of host reads (validated on device)
 FUSED_BLOCKS = True  # training-mode residual blocks through b2s_resblock_forward/backward (host-side fusion)
 
 
@@ -96,8 +97,11 @@ class Backbone(nn.Module):
         self.offset_branch = nn.Sequential(nn.Linear(m, m), nn.BatchNorm1d(m), nn.ReLU(inplace=True),
                                            nn.Linear(m, 3))
 
-    def forward(self, voxel_features, voxel_coordinates, v2p_map):
-        x = ME.SparseTensor(features=voxel_features, coordinates=voxel_coordinates)
+    def forward(self, voxel_features, voxel_coordinates, v2p_map, level_sizes=None):
+        # the loader's voxels are unique by construction (sparse_quantize) and it reports the level sizes: no host
+        # read of device counts in the whole backbone, the host keeps enqueuing while the GPU finishes the last step
+        x = ME.SparseTensor(features=voxel_features, coordinates=voxel_coordinates,
+                            coordinates_unique=level_sizes is not None, level_sizes=level_sizes)
         unet_out = self.unet(x)
         point_features = ops.devoxelize(unet_out.features, v2p_map)  # == features[v2p_map], backbone.py:40
         return {"point_features": point_features,
@@ -200,7 +204,9 @@ def clusters_voxelization(clusters_idx, clusters_offset, feats, coords, scale, s
     batched_xyz = ops.clusters_voxelize(clusters_idx.contiguous(), clusters_offset, coords, scale, spatial_shape, rand)
     voxel_xyz, voxel_features, _, voxel_point_map = ME.utils.sparse_quantize(
         batched_xyz, feats, return_index=True, return_inverse=True, device="cuda")
-    return ME.SparseTensor(features=voxel_features, coordinates=voxel_xyz, device=device), voxel_point_map
+    # sparse_quantize output is unique by construction: no second host read for the row count
+    return ME.SparseTensor(features=voxel_features, coordinates=voxel_xyz, device=device,
+                           coordinates_unique=ASYNC_SIZES), voxel_point_map
 
 
 def get_segmented_scores(scores, fg_thresh=1.0, bg_thresh=0.0):
@@ -233,7 +239,8 @@ class GeneralModel(nn.Module):
         self.clustering = True  # current_epoch > prepare_epochs
 
     def backbone_forward(self, data):
-        return self.backbone(data["voxel_features"], data["voxel_xyz"], data["voxel_point_map"])
+        return self.backbone(data["voxel_features"], data["voxel_xyz"], data["voxel_point_map"],
+                             data.get("voxel_level_sizes") if ASYNC_SIZES else None)
 
     def base_loss(self, data, out):
         losses = {"semantic_loss": F.cross_entropy(out["semantic_scores"], data["sem_labels"].long(), ignore_index=-1)}

@@ -144,7 +144,18 @@ def collate(scenes, device, quantize_device=None):
     bcoords, bfeats = me_utils.sparse_collate(out["voxel_xyz"], out["voxel_features"])
     data["voxel_xyz"] = bcoords.to(device)
     data["voxel_features"] = bfeats.to(device)
+    if device.type == "cuda":
+        data["voxel_level_sizes"] = level_sizes(data["voxel_xyz"])
     return data
+
+
+def level_sizes(voxel_xyz, levels=6):
+    """{tensor stride: rows} of the strided coordinate maps of a voxelised batch -- a by-product of voxelisation that
+    the loader hands to the model as host metadata (like the reference's loader hands over `voxel_point_map`), so
+    that the MinkUNet forward needs no host read of device-side counts.  The model still builds every map on the
+    device and validates these numbers there (ops.run_deferred_checks)."""
+    from .. import ops
+    return {int(s): int(oc.size(0)) for s, _, oc in ops.coord_pyramid(voxel_xyz.contiguous(), 1, levels)}
 
 
 def make_batch(seeds, device, n_points=100_000):

@@ -6,7 +6,7 @@ scene-sharded gradient all-reduce (minsu3d_b200.dp) and Adam (config/model/point
 """
 import torch
 
-from .. import dp
+from .. import dp, ops
 from . import models
 
 HOST_KEYS = ("point_xyz", "vert_batch_ids", "sem_labels", "instance_ids", "instance_center_xyz",
@@ -66,4 +66,6 @@ class Trainer:
     def step_from_host(self, host_data):
         """The user-facing call: pinned host batch in, python float loss out (H2D + D2H inside)."""
         data = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_data.items()}
-        return float(self.step(data).item())
+        loss = float(self.step(data).item())
+        ops.run_deferred_checks()  # size claims of this step (loader-reported level sizes), stream already drained
+        return loss

@@ -53,21 +53,57 @@ def coord_unique_async(coords, quant=1, d_n=None):
     return table, unique_idx, inverse, out_coords, d_count
 
 
-def coord_unique(coords, quant=1):
+# Deferred validation of device-side counts.  Data-dependent sizes normally cost a host read (the GPU drains, the
+# host loses its run-ahead); when the caller KNOWS the size (coordinates that are unique by construction, level
+# sizes the voxeliser reported) the read is skipped, the device count is kept, and it is compared with the claim
+# at the next host read that happens anyway.  A wrong claim raises there -- it is never silently accepted.
+_RANGE_MSG = "coordinate outside the packable range (batch < 2^19, |xyz| < 2^14)"
+_DEFERRED = []  # (d_count int32[2] = {m, range_error}, expected m, what)
+
+
+def defer_count_check(d_count, expected, what):
+    _DEFERRED.append((d_count, int(expected), what))
+    if len(_DEFERRED) >= 256:  # nobody synchronised for a long time: do it now
+        run_deferred_checks()
+
+
+def run_deferred_checks():
+    """Validate the pending size claims; call right after a host read (the stream is drained, this is cheap)."""
+    if not _DEFERRED:
+        return
+    items = _DEFERRED[:]
+    del _DEFERRED[:]
+    vals = torch.stack([d for d, _, _ in items]).tolist()
+    for (m, bad), (_, expected, what) in zip(vals, items):
+        if bad:
+            raise ValueError(_RANGE_MSG)
+        if m != expected:
+            raise ValueError("%s: claimed %d rows but the device counted %d" % (what, expected, m))
+
+
+def coord_unique(coords, quant=1, assume_unique=False):
     """First-occurrence unique of int32 [n,4] coordinates (optionally floor-quantised).
 
-    Returns (table, unique_idx[m] i32, inverse[n] i32, out_coords[m,4] i32).  One host read of m.
+    Returns (table, unique_idx[m] i32, inverse[n] i32, out_coords[m,4] i32).  One host read of m -- unless
+    assume_unique: the caller states that the rows are already unique (m == n), no host read happens and the
+    statement is validated later (run_deferred_checks).
     """
     table, unique_idx, inverse, out_coords, d_count = coord_unique_async(coords, quant)
+    if assume_unique:
+        defer_count_check(d_count, coords.size(0), "SparseTensor(coordinates_unique=True)")
+        return table, unique_idx, inverse, out_coords
     m, bad = d_count.tolist()
+    run_deferred_checks()
     if bad:
-        raise ValueError("coordinate outside the packable range (batch < 2^19, |xyz| < 2^14)")
+        raise ValueError(_RANGE_MSG)
     return table, unique_idx[:m], inverse, out_coords[:m]
 
 
-def coord_pyramid(coords, base_stride, levels):
+def coord_pyramid(coords, base_stride, levels, size_hints=None):
     """Strided maps base*2, base*4, ... built back to back on the device; ONE host read for all counts.
 
+    size_hints: the row counts of the levels as reported by whoever voxelised the scene (a by-product of the data
+    loader's quantisation); then there is NO host read, the device counts are validated later.
     Returns a list of (stride, table, out_coords[m_l, 4]).
     """
     out, d_counts = [], []
@@ -78,9 +114,15 @@ def coord_pyramid(coords, base_stride, levels):
         out.append((stride, table, oc))
         d_counts.append(d_count)
         cur, d_n = oc, d_count
+    if size_hints is not None:
+        require(len(size_hints) >= levels, "size_hints must cover every level")
+        for (s, _, _), d_count, m in zip(out, d_counts, size_hints):
+            defer_count_check(d_count, m, "coordinate map of tensor stride %d (size hint)" % s)
+        return [(s, t, oc[:int(m)]) for (s, t, oc), m in zip(out, size_hints)]
     counts = torch.stack(d_counts).tolist()
+    run_deferred_checks()
     if any(bad for _, bad in counts):
-        raise ValueError("coordinate outside the packable range (batch < 2^19, |xyz| < 2^14)")
+        raise ValueError(_RANGE_MSG)
     return [(s, t, oc[:m]) for (s, t, oc), (m, _) in zip(out, counts)]
 
 
@@ -358,6 +400,7 @@ def ballquery(coords, batch_idxs, batch_offsets, radius):
     check(lib().b2s_ballquery_count(ptr(coords), ptr(batch_idxs), ptr(batch_offsets), n, nb, float(radius),
                                     ptr(start_len), ptr(d_count), ptr(ws), ws.numel(), stream()), "ballquery_count")
     n_active = int(d_count.item()) if n > 0 else 0
+    run_deferred_checks()
     idx = _dev_i32(n_active, dev)
     if n_active > 0:
         check(lib().b2s_ballquery_fill(ptr(coords), ptr(batch_idxs), ptr(batch_offsets), n, nb, float(radius),
@@ -394,6 +437,7 @@ def cluster_extract(nbr_idx, start_len, labels, comp, mode, thr_i=0, thr_f=0.0, 
                                    group, ptr(offsets), ptr(seeds), ptr(d_count), ptr(ws), ws.numel(), stream()),
           "cluster_select")
     n_cluster, total = d_count.tolist()
+    run_deferred_checks()
     cluster_idxs = torch.empty((total, 2), dtype=I32, device=dev)
     offsets = offsets[:n_cluster + 1]
     if n_cluster > 0:

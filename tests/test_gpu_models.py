@@ -218,3 +218,34 @@ def test_fused_blocks_fall_back_in_eval_mode(batch, monkeypatch):
         with torch.no_grad():
             outs.append(blk(ME.SparseTensor(features=x, coordinates=coords)).F)
     assert torch.equal(outs[0], outs[1])
+
+
+def test_loader_size_hints_remove_host_reads_and_are_validated(batch):
+    """SparseTensor(coordinates_unique=True, level_sizes=...) skips the host reads of the device-side counts; the
+    claims are checked on the device: identical backbone output when they hold, ValueError when they do not."""
+    from minsu3d_b200 import MinkowskiEngine as ME, ops
+    from minsu3d_b200.harness import models, scenes
+    torch.manual_seed(123)
+    model = models.build_model(models.Config.for_model("pointgroup")).cuda().train()
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    sizes = batch["voxel_level_sizes"]
+    assert sorted(sizes) == [2, 4, 8, 16, 32, 64] and all(v > 0 for v in sizes.values())
+    outs = []
+    for hints in (None, sizes):
+        model.load_state_dict(state)
+        outs.append(model.backbone(batch["voxel_features"], batch["voxel_xyz"], batch["voxel_point_map"], hints))
+        ops.run_deferred_checks()
+    for k in ("point_features", "semantic_scores", "point_offsets"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    # a wrong level size is detected on the device
+    bad = dict(sizes)
+    bad[4] -= 1
+    model.backbone(batch["voxel_features"], batch["voxel_xyz"], batch["voxel_point_map"], bad)
+    with pytest.raises(ValueError, match="claimed"):
+        ops.run_deferred_checks()
+    # duplicated coordinates passed as unique are detected too
+    c = torch.cat((batch["voxel_xyz"][:100], batch["voxel_xyz"][:5])).contiguous()
+    ME.SparseTensor(features=torch.zeros(105, 4, device="cuda"), coordinates=c, coordinates_unique=True)
+    with pytest.raises(ValueError, match="claimed"):
+        ops.run_deferred_checks()
+    ops.run_deferred_checks()  # the list is empty again
