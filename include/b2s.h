@@ -311,7 +311,27 @@ int b2s_get_mask_label(const int32_t* proposals_idx, const int32_t* proposals_of
                        int32_t ignored_label, float iou_thr, uint8_t* mask_label,
                        uint8_t* mask_label_mask, b2s_stream_t stream);
 
-
+/* ------------------------------------------------------------------------------------------------
+ * instance post-processing on the device -- PointGroup._get_pred_instances /
+ * _get_nms_instances (minsu3d/model/pointgroup.py:197-265) and HAIS._get_pred_instances
+ * (minsu3d/model/hais.py:210-247) without the dense [nProposal, N] masks and the CPU round trip.
+ *   b2s_proposal_sort : keys_sorted [S] uint64 = sorted (point << 32 | proposal) of the pairs with valid[i] != 0
+ *                       (valid == NULL: all; HAIS mask-score filter, hais.py:222-223); dropped pairs sort last
+ *   b2s_proposal_npoint: npoint [nProposal] = distinct points per proposal (= mask.sum(1))
+ *   b2s_proposal_iou  : remap [nProposal] = row of the proposal among the kept ones or -1;
+ *                       inter [n_kept, n_kept] int32 = mask @ mask.T, iou = inter / (n_a + n_b - inter) (fp32)
+ *   b2s_nms           : greedy suppression in the given order (descending score): pick [<= n], d_count = picks;
+ *                       ws >= n bytes
+ * ---------------------------------------------------------------------------------------------- */
+size_t b2s_proposal_sort_ws_bytes(int64_t S);
+int b2s_proposal_sort(const int32_t* prop_idx, const uint8_t* valid, int64_t S, uint64_t* keys_sorted, void* ws,
+                      size_t ws_bytes, b2s_stream_t stream);
+int b2s_proposal_npoint(const uint64_t* keys_sorted, int64_t S, int32_t n_proposal, int32_t* npoint,
+                        b2s_stream_t stream);
+int b2s_proposal_iou(const uint64_t* keys_sorted, int64_t S, const int32_t* remap, int32_t n_kept, int32_t* inter,
+                     float* iou, b2s_stream_t stream);
+int b2s_nms(const float* iou, const int32_t* order, int32_t n, float threshold, int32_t* pick, int32_t* d_count,
+            void* ws, size_t ws_bytes, b2s_stream_t stream);
 
 #ifdef __cplusplus
 }

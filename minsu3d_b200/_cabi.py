@@ -69,6 +69,11 @@ _SIGNATURES = {
     "b2s_global_avg_pool_fp": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
     "b2s_global_avg_pool_bp": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
     "b2s_clusters_voxelize": (c_i32, [_P, c_i32, _P, c_i64, c_i32, _P, c_f32, c_i32, _P, _P, _P, _P]),
+    "b2s_proposal_sort_ws_bytes": (c_size, [c_i64]),
+    "b2s_proposal_sort": (c_i32, [_P, _P, c_i64, _P, _P, c_size, _P]),
+    "b2s_proposal_npoint": (c_i32, [_P, c_i64, c_i32, _P, _P]),
+    "b2s_proposal_iou": (c_i32, [_P, c_i64, _P, c_i32, _P, _P, _P]),
+    "b2s_nms": (c_i32, [_P, _P, c_i32, c_f32, _P, _P, _P, c_size, _P]),
     "b2s_get_iou": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, _P]),
     "b2s_get_mask_label": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_f32, _P, _P, _P]),
 }
@@ -109,7 +114,7 @@ KERNELS_PER_CALL = {
     "b2s_cluster_select": 7, "b2s_cluster_order": 4, "b2s_cluster_centers": 1, "b2s_ha_assign": 1,
     "b2s_ha_concat": 4, "b2s_sec_mean": 1, "b2s_sec_min": 1, "b2s_sec_max": 1, "b2s_roipool_fp": 1,
     "b2s_roipool_bp": 1, "b2s_global_avg_pool_fp": 1, "b2s_global_avg_pool_bp": 1, "b2s_get_iou": 1, "b2s_clusters_voxelize": 2,
-    "b2s_get_mask_label": 1,
+    "b2s_get_mask_label": 1, "b2s_proposal_sort": 10, "b2s_proposal_npoint": 1, "b2s_proposal_iou": 2, "b2s_nms": 1,
 }
 _launches = [0]
 

@@ -324,3 +324,37 @@ def test_segmented_scores_and_offset_loss_helpers():
     n, d = models.pt_offset_loss(torch.ones(4, 3), torch.ones(4, 3), torch.tensor([True, True, False, True]))
     assert float(n) == 0.0 and abs(float(d) + 1.0) < 1e-6
     assert models.pt_offset_loss(torch.ones(2, 3), torch.ones(2, 3), torch.tensor([False, False])) == (0, 0)
+
+
+# ------------------------------------------------------------------------------------------
+# post-processing restatement pinned by the reference's own methods
+# ------------------------------------------------------------------------------------------
+def _postproc_case(g, ci):
+    return {k[len("c%d_in_" % ci):]: g[k] for k in g.files if k.startswith("c%d_in_" % ci)}
+
+
+def _check_instances(got, g, prefix):
+    assert np.array_equal(np.asarray(got["label_id"]), g[prefix + "label_id"])
+    assert np.allclose(np.asarray(got["conf"]), g[prefix + "conf"], rtol=0, atol=1e-6)
+    assert np.array_equal(np.asarray(got["bbox"]), g[prefix + "bbox"])
+    assert np.array_equal(np.asarray(got["mask_offsets"]), g[prefix + "mask_offsets"])
+    assert np.array_equal(np.asarray(got["mask_points"]), g[prefix + "mask_points"])
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_postproc_oracle_matches_reference_methods(ci):
+    """oracle.postproc vs outputs of PointGroup._get_pred_instances/_get_nms_instances and
+    HAIS._get_pred_instances run from /root/reference (tests/golden/make_postproc_golden.py)."""
+    from oracle import postproc
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "postproc_ref.npz"))
+    c = _postproc_case(g, ci)
+    sem = c["semantic_labels"].astype(np.int64)
+    pg = postproc.pointgroup_pred_instances(c["xyz"], c["scores"], c["proposals_idx"], int(c["n_proposals"]), sem,
+                                            int(c["num_ignored"]), float(c["score_thr"]), int(c["npoint_thr"]),
+                                            float(c["nms_thr"]))
+    _check_instances(pg, g, "c%d_pg_" % ci)
+    assert pg["label_id"].size > 0
+    hs = postproc.hais_pred_instances(c["xyz"], c["scores"], c["proposals_idx"], int(c["n_proposals"]),
+                                      c["mask_scores"], sem, int(c["num_ignored"]), float(c["mask_thr"]),
+                                      float(c["score_thr"]), int(c["npoint_thr"]))
+    _check_instances(hs, g, "c%d_hais_" % ci)

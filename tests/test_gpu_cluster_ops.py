@@ -363,3 +363,89 @@ def test_soft_grouping_all_classes_in_one_pass_matches_the_per_class_loop():
     assert torch.equal(got[1], want[1])
     assert torch.equal(got[0], want[0])
     assert want[1].numel() - 1 >= 4  # several proposals, from more than one class
+
+
+# ------------------------------------------------------------------------------------------
+# instance post-processing on the device vs the oracle and the reference goldens
+# ------------------------------------------------------------------------------------------
+def _pp_check(got, want, conf_tol=1e-6):
+    g = {k: v.cpu().numpy() for k, v in got.items()}
+    assert np.array_equal(g["proposal"], np.asarray(want["proposal"])) if "proposal" in want else True
+    assert np.array_equal(g["label_id"], np.asarray(want["label_id"]))
+    assert np.allclose(g["conf"], np.asarray(want["conf"]), rtol=0, atol=conf_tol)
+    assert np.array_equal(g["bbox"], np.asarray(want["bbox"]))
+    assert np.array_equal(g["mask_offsets"], np.asarray(want["mask_offsets"]))
+    assert np.array_equal(g["mask_points"], np.asarray(want["mask_points"]))
+
+
+def _pp_inputs(c):
+    import torch
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    sem_scores = np.eye(20, dtype=np.float32)[np.asarray(c["semantic_labels"]).astype(np.int64)]
+    return d(c["xyz"]), d(c["scores"]), d(c["proposals_idx"]), int(c["n_proposals"]), d(sem_scores), d(c["mask_scores"])
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_postprocess_matches_reference_goldens_and_oracle(ci):
+    """PointGroup NMS path and HAIS filter path on the device = the reference's own methods (golden) = oracle."""
+    import os
+    from minsu3d_b200 import postprocess
+    from oracle import postproc
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "postproc_ref.npz"))
+    c = {k[len("c%d_in_" % ci):]: g[k] for k in g.files if k.startswith("c%d_in_" % ci)}
+    xyz, scores, pidx, n_prop, sem_scores, mask_scores = _pp_inputs(c)
+    args = (int(c["num_ignored"]), float(c["score_thr"]), int(c["npoint_thr"]))
+    got = postprocess.pointgroup_pred_instances(xyz, scores, pidx, n_prop, sem_scores, *args, float(c["nms_thr"]))
+    _pp_check(got, {k: g["c%d_pg_%s" % (ci, k)] for k in ("label_id", "conf", "bbox", "mask_offsets", "mask_points")})
+    sem = np.asarray(c["semantic_labels"]).astype(np.int64)
+    _pp_check(got, postproc.pointgroup_pred_instances(c["xyz"], c["scores"], c["proposals_idx"], n_prop, sem, *args,
+                                                      float(c["nms_thr"])))
+    got = postprocess.hais_pred_instances(xyz, scores, pidx, n_prop, mask_scores, sem_scores, int(c["num_ignored"]),
+                                          float(c["mask_thr"]), float(c["score_thr"]), int(c["npoint_thr"]))
+    _pp_check(got, {k: g["c%d_hais_%s" % (ci, k)] for k in ("label_id", "conf", "bbox", "mask_offsets", "mask_points")})
+    # the reference's list-of-dicts format incl. RLE strings round-trips to the same masks
+    ref_fmt = postprocess.to_reference_format(got, "scene0000_00", int(np.asarray(c["xyz"]).shape[0]))
+    assert len(ref_fmt) == got["label_id"].numel()
+    if ref_fmt:
+        runs = np.array(ref_fmt[0]["pred_mask"]["counts"].split(), np.int64)
+        assert runs[1::2].sum() == int(got["mask_offsets"][1])
+
+
+def test_postprocess_large_duplicates_and_empty():
+    """200k points / 400 overlapping proposals with duplicated pairs (the dense mask is a set) vs the oracle;
+    integer intermediates (npoint, intersections) bit-exact, IoU the same fp32 expression; nothing passes -> empty."""
+    import torch
+    from minsu3d_b200 import postprocess
+    from oracle import postproc
+    rng = np.random.default_rng(7)
+    n, n_prop = 200_000, 400
+    centers = rng.integers(0, n, n_prop)
+    rows = []
+    for p in range(n_prop):
+        size = int(rng.integers(20, 3000))
+        pts = (centers[p // 2 * 2] + rng.integers(-2000, 2000, size)) % n  # pairs of proposals share a neighbourhood
+        rows.append(np.stack((np.full(size, p), pts), 1))  # rng.integers repeats points: duplicated pairs
+    pidx = np.concatenate(rows).astype(np.int32)
+    xyz = rng.uniform(-5, 5, (n, 3)).astype(np.float32)
+    scores = rng.normal(0, 2, (n_prop, 1)).astype(np.float32)
+    sem = rng.integers(0, 20, n)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    keys = postprocess._sorted_keys(d(pidx))
+    mask = np.zeros((n_prop, n), bool)
+    mask[pidx[:, 0], pidx[:, 1]] = True
+    npoint = postprocess.proposal_npoint(keys, n_prop)
+    assert np.array_equal(npoint.cpu().numpy(), mask.sum(1))
+    keep = mask.sum(1) > 100
+    ids, inter, iou = postprocess.proposal_cross_iou(keys, d(keep))
+    mf = mask[keep].astype(np.float32)
+    want_inter = mf @ mf.T
+    assert np.array_equal(inter.cpu().numpy(), want_inter.astype(np.int32))
+    npf = mf.sum(1)
+    assert np.array_equal(iou.cpu().numpy(), want_inter / (npf[:, None] + npf[None, :] - want_inter))
+    sem_scores = np.eye(20, dtype=np.float32)[sem]
+    got = postprocess.pointgroup_pred_instances(d(xyz), d(scores), d(pidx), n_prop, d(sem_scores), 2, 0.09, 100, 0.3)
+    want = postproc.pointgroup_pred_instances(xyz, scores, pidx, n_prop, sem, 2, 0.09, 100, 0.3)
+    assert want["label_id"].size > 20
+    _pp_check(got, want)
+    got = postprocess.pointgroup_pred_instances(d(xyz), d(scores), d(pidx), n_prop, d(sem_scores), 2, 0.09, 10**6, 0.3)
+    assert got["label_id"].numel() == 0 and got["bbox"].shape == (0, 6) and got["mask_offsets"].tolist() == [0]
