@@ -1,7 +1,8 @@
 """Instance post-processing on the device.
 
-Replaces `PointGroup._get_pred_instances` + `_get_nms_instances` (minsu3d/model/pointgroup.py:197-265) and
-`HAIS._get_pred_instances` (minsu3d/model/hais.py:210-247): the reference moves everything to the CPU, builds dense
+Replaces `PointGroup._get_pred_instances` + `_get_nms_instances` (minsu3d/model/pointgroup.py:197-265),
+`HAIS._get_pred_instances` (minsu3d/model/hais.py:210-247) and `SoftGroup._get_pred_instances`
+(minsu3d/model/softgroup.py:269-313): the reference moves everything to the CPU, builds dense
 bool masks [nProposal, N], multiplies them (torch.mm) for the cross IoUs and runs a numpy NMS loop.  Here the
 (proposal, point) pair list is sorted once on the GPU (csrc/postproc.cu) and distinct-point counts, the
 intersection matrix, the IoUs and the NMS come out of it; labels and boxes are segmented reductions.
@@ -74,8 +75,9 @@ def nms(cross_ious, scores, threshold):
     return pick[:int(d_count.item())].long()
 
 
-def _instances(keys, ids, conf, xyz, sem_labels, num_ignored, num_proposals):
-    """Labels, boxes and point lists of the proposals `ids` (in that order) from the sorted distinct pairs."""
+def _instances(keys, ids, conf, xyz, sem_labels, num_ignored, num_proposals, label=None):
+    """Labels, boxes and point lists of the proposals `ids` (in that order) from the sorted distinct pairs.
+    label: fixed label id for every instance (SoftGroup) instead of the semantic label of the first point."""
     dev = keys.device
     n = ids.numel()
     valid = keys != -1
@@ -99,8 +101,11 @@ def _instances(keys, ids, conf, xyz, sem_labels, num_ignored, num_proposals):
         out["label_id"] = torch.zeros(0, dtype=torch.int64, device=dev)
         out["bbox"] = torch.zeros((0, 6), dtype=torch.float32, device=dev)
         return out
-    first = point[offsets[:-1].long()]  # lowest point index of each instance (semantic_pred_labels[mask][0])
-    out["label_id"] = sem_labels[first].long() - num_ignored + 1
+    if label is not None:
+        out["label_id"] = torch.full((n,), int(label), dtype=torch.int64, device=dev)
+    else:
+        first = point[offsets[:-1].long()]  # lowest point index of each instance (semantic_pred_labels[mask][0])
+        out["label_id"] = sem_labels[first].long() - num_ignored + 1
     pts = xyz[point].contiguous()
     lo = torch.empty((n, 3), dtype=torch.float32, device=dev)
     hi = torch.empty((n, 3), dtype=torch.float32, device=dev)
@@ -133,6 +138,39 @@ def hais_pred_instances(xyz, scores, proposals_idx, num_proposals, mask_scores, 
     npoint = proposal_npoint(keys, num_proposals)
     ids = torch.nonzero((score > score_thr) & (npoint >= npoint_thr)).view(-1)
     return _instances(keys, ids, score[ids], xyz, sem_labels, num_ignored, num_proposals)
+
+
+def softgroup_pred_instances(xyz, proposals_idx, num_points, cls_scores, iou_scores, mask_scores, instance_classes,
+                             mask_thr, cls_thr, min_npoint):
+    """softgroup.py:269-313: one filter pass per instance class that has any proposal above the class-score
+    threshold (one host read decides which); output ordered by class, then proposal; label_id = class + 1."""
+    num_instances = cls_scores.size(0)
+    cls = cls_scores.softmax(1)
+    above = cls[:, :instance_classes] > cls_thr
+    active = above.any(0).tolist()
+    parts = []
+    for i in range(instance_classes):
+        if not active[i]:
+            continue
+        keys = _sorted_keys(proposals_idx, valid=mask_scores[:, i] > mask_thr)
+        npoint = proposal_npoint(keys, num_instances)
+        ids = torch.nonzero(above[:, i] & (npoint >= min_npoint)).view(-1)
+        if ids.numel() == 0:
+            continue
+        score = cls[:, i] * iou_scores[:, i].clamp(0, 1)
+        parts.append(_instances(keys, ids, score[ids], xyz, None, 0, num_instances, label=i + 1))
+    dev = cls_scores.device
+    if not parts:
+        return {"proposal": torch.zeros(0, dtype=I32, device=dev), "label_id": torch.zeros(0, dtype=torch.int64, device=dev),
+                "conf": torch.zeros(0, dtype=torch.float32, device=dev),
+                "bbox": torch.zeros((0, 6), dtype=torch.float32, device=dev),
+                "mask_points": torch.zeros(0, dtype=I32, device=dev), "mask_offsets": torch.zeros(1, dtype=I32, device=dev)}
+    out = {k: torch.cat([p[k] for p in parts]) for k in ("proposal", "label_id", "conf", "bbox", "mask_points")}
+    counts = torch.cat([(p["mask_offsets"][1:] - p["mask_offsets"][:-1]) for p in parts])
+    offsets = torch.zeros(counts.numel() + 1, dtype=I32, device=dev)
+    offsets[1:] = torch.cumsum(counts, 0)
+    out["mask_offsets"] = offsets
+    return out
 
 
 def to_reference_format(result, scan_id, num_points):

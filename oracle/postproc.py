@@ -87,3 +87,48 @@ def hais_pred_instances(xyz, scores, proposals_idx, num_proposals, mask_scores, 
     sel = mask.sum(1) >= npoint_thr
     score, mask, ids = score[sel], mask[sel], ids[sel]
     return _instances(mask, ids, score, xyz, sem_labels, num_ignored)
+
+
+def _softmax(x):
+    x = np.asarray(x, np.float32)
+    e = np.exp(x - x.max(1, keepdims=True), dtype=np.float32)
+    return (e / e.sum(1, keepdims=True, dtype=np.float32)).astype(np.float32)
+
+
+def _concat(parts, n_label_dtype=np.int64):
+    out = {"proposal": np.concatenate([p["proposal"] for p in parts]) if parts else np.zeros(0, np.int32),
+           "label_id": np.concatenate([p["label_id"] for p in parts]) if parts else np.zeros(0, n_label_dtype),
+           "conf": np.concatenate([p["conf"] for p in parts]) if parts else np.zeros(0, np.float32),
+           "bbox": np.concatenate([p["bbox"] for p in parts]) if parts else np.zeros((0, 6), np.float32),
+           "mask_points": np.concatenate([p["mask_points"] for p in parts]) if parts else np.zeros(0, np.int32)}
+    offs = [np.zeros(1, np.int64)]
+    base = 0
+    for p in parts:
+        offs.append(p["mask_offsets"][1:].astype(np.int64) + base)
+        base += int(p["mask_offsets"][-1])
+    out["mask_offsets"] = np.concatenate(offs).astype(np.int32)
+    return out
+
+
+def softgroup_pred_instances(xyz, proposals_idx, num_points, cls_scores, iou_scores, mask_scores, instance_classes,
+                             mask_thr, cls_thr, min_npoint):
+    """softgroup.py:269-313: per instance class, proposals above the class-score threshold with at least
+    min_npoint points whose class mask score passes; conf = softmax class score * clamp(iou score, 0, 1);
+    label_id = class + 1; output ordered by class, then proposal."""
+    num_instances = cls_scores.shape[0]
+    cls = _softmax(cls_scores)
+    parts = []
+    for i in range(instance_classes):
+        score = cls[:, i] * np.clip(np.asarray(iou_scores, np.float32)[:, i], 0, 1)
+        mask = np.zeros((num_instances, num_points), bool)
+        ok = np.asarray(mask_scores, np.float32)[:, i] > np.float32(mask_thr)
+        mask[proposals_idx[ok][:, 0], proposals_idx[ok][:, 1]] = True
+        ids = np.arange(num_instances)
+        sel = cls[:, i] > np.float32(cls_thr)
+        score, mask, ids = score[sel], mask[sel], ids[sel]
+        sel = mask.sum(1) >= min_npoint
+        score, mask, ids = score[sel], mask[sel], ids[sel]
+        part = _instances(mask, ids, score, xyz, np.zeros(num_points, np.int64), 0)
+        part["label_id"][:] = i + 1
+        parts.append(part)
+    return _concat(parts)

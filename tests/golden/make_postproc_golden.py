@@ -1,7 +1,8 @@
 """Generates tests/golden/postproc_ref.npz by RUNNING the reference's own post-processing methods.
 
-SURVEY 8(f) #2: `PointGroup._get_nms_instances` / `_get_pred_instances` (minsu3d/model/pointgroup.py:197-265) and
-`HAIS._get_pred_instances` (minsu3d/model/hais.py:210-247).  The model modules import Lightning (not installed), so
+SURVEY 8(f) #2: `PointGroup._get_nms_instances` / `_get_pred_instances` (minsu3d/model/pointgroup.py:197-265),
+`HAIS._get_pred_instances` (minsu3d/model/hais.py:210-247) and `SoftGroup._get_pred_instances`
+(minsu3d/model/softgroup.py:269-313).  The model modules import Lightning (not installed), so
 the two classes cannot be imported; instead the method sources are pulled out of the reference files with `ast` at
 generation time and executed unchanged against a stub `self` (nothing of the reference is copied into this repo).
 
@@ -19,6 +20,9 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from helpers import sg_mask_scores  # noqa: E402
+
 REF = os.environ.get("MINSU3D_REFERENCE", "/root/reference")
 
 
@@ -90,6 +94,18 @@ def run_hais(case, m):
                                     case["num_ignored"])
 
 
+def run_softgroup(case, m):
+    ns = types.SimpleNamespace
+    self = ns(instance_classes=case["instance_classes"],
+              hparams=ns(cfg=ns(model=ns(network=ns(test_cfg=ns(mask_score_thr=case["mask_thr"],
+                                                                cls_score_thr=case["cls_thr"],
+                                                                min_npoint=case["npoint_thr"]))))))
+    return m["_get_pred_instances"](self, "scene0000_00", case["xyz"], torch.from_numpy(case["proposals_idx"]).long(),
+                                    case["xyz"].shape[0], torch.from_numpy(case["sg_cls_scores"]),
+                                    torch.from_numpy(case["sg_iou_scores"]), torch.from_numpy(case["sg_mask_scores"]),
+                                    case["num_ignored"])
+
+
 def pack(inst, rle_decode, n_points):
     """list of pred dicts -> arrays (masks as sorted point lists in CSR form)."""
     label = np.array([int(d["label_id"]) for d in inst], np.int64)
@@ -109,6 +125,7 @@ def pack(inst, rle_decode, n_points):
 def main():
     pg = reference_methods("minsu3d/model/pointgroup.py", "PointGroup", ("_get_nms_instances", "_get_pred_instances"))
     hs = reference_methods("minsu3d/model/hais.py", "HAIS", ("_get_pred_instances",))
+    sg = reference_methods("minsu3d/model/softgroup.py", "SoftGroup", ("_get_pred_instances",))
     out = {}
     for ci, (n_points, n_obj, per_obj, seed) in enumerate(((4000, 6, 3, 1), (20000, 25, 4, 2), (500, 1, 1, 3))):
         rng = np.random.default_rng(seed)
@@ -119,13 +136,19 @@ def main():
                 "semantic_labels": rng.integers(0, 20, n_points).astype(np.int8),
                 "mask_scores": rng.normal(0.3, 1.0, (pidx.shape[0], 1)).astype(np.float32),
                 "num_ignored": 2, "nms_thr": 0.3, "score_thr": 0.09, "npoint_thr": 100 if n_points > 1000 else 10,
-                "mask_thr": -0.5}
+                "mask_thr": -0.5, "instance_classes": 18, "cls_thr": 0.05}
+        # SoftGroup heads: class scores [P, 19] (softmax incl. background), IoU scores [P, 19], point mask scores [S, 19]
+        case["sg_cls_scores"] = rng.normal(0, 2.0, (n_prop, 19)).astype(np.float32)
+        case["sg_iou_scores"] = rng.uniform(-0.3, 1.3, (n_prop, 19)).astype(np.float32)
+        case["sg_seed"] = seed  # sg_mask_scores = helpers.sg_mask_scores(seed, S): regenerated by the tests, not stored
         for k, v in case.items():
             out["c%d_in_%s" % (ci, k)] = np.asarray(v)
+        case["sg_mask_scores"] = sg_mask_scores(seed, pidx.shape[0])
         # the reference takes scores and arg-maxes them; one-hot scores keep the fixture small
         case["semantic_scores"] = np.eye(20, dtype=np.float32)[case["semantic_labels"].astype(np.int64)]
         for name, res in (("pg", pack(run_pointgroup(case, pg), pg["rle_decode"], n_points)),
-                          ("hais", pack(run_hais(case, hs), hs["rle_decode"], n_points))):
+                          ("hais", pack(run_hais(case, hs), hs["rle_decode"], n_points)),
+                          ("sg", pack(run_softgroup(case, sg), sg["rle_decode"], n_points))):
             for k, v in res.items():
                 out["c%d_%s_%s" % (ci, name, k)] = v
             print("case", ci, name, "proposals", n_prop, "instances", res["label_id"].size)

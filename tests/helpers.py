@@ -49,3 +49,10 @@ def clustered_points(rng, n, n_obj=12, batch=2, spread=0.05, collapse=False):
 def canon_clusters(cluster_idxs, cluster_offsets):
     """Order-independent view: list of sorted point arrays in cluster order."""
     return [np.sort(cluster_idxs[cluster_offsets[i]:cluster_offsets[i + 1], 1]) for i in range(len(cluster_offsets) - 1)]
+
+
+def sg_mask_scores(seed, n_pairs, n_cls=19):
+    """SoftGroup point-mask scores [S, classes+1] of the post-processing fixtures: regenerated from the seed on both
+    sides (tests/golden/make_postproc_golden.py and the tests) instead of being stored (3 MB)."""
+    rng = np.random.default_rng(10_000 + seed)
+    return rng.normal(0.3, 1.0, (n_pairs, n_cls)).astype(np.float32)

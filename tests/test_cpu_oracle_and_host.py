@@ -358,3 +358,10 @@ def test_postproc_oracle_matches_reference_methods(ci):
                                       c["mask_scores"], sem, int(c["num_ignored"]), float(c["mask_thr"]),
                                       float(c["score_thr"]), int(c["npoint_thr"]))
     _check_instances(hs, g, "c%d_hais_" % ci)
+    from helpers import sg_mask_scores
+    sg = postproc.softgroup_pred_instances(c["xyz"], c["proposals_idx"], c["xyz"].shape[0], c["sg_cls_scores"],
+                                           c["sg_iou_scores"], sg_mask_scores(int(c["sg_seed"]), c["proposals_idx"].shape[0]),
+                                           int(c["instance_classes"]), float(c["mask_thr"]), float(c["cls_thr"]),
+                                           int(c["npoint_thr"]))
+    _check_instances(sg, g, "c%d_sg_" % ci)
+    assert sg["label_id"].size > 0

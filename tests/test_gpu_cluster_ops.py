@@ -403,6 +403,14 @@ def test_postprocess_matches_reference_goldens_and_oracle(ci):
     got = postprocess.hais_pred_instances(xyz, scores, pidx, n_prop, mask_scores, sem_scores, int(c["num_ignored"]),
                                           float(c["mask_thr"]), float(c["score_thr"]), int(c["npoint_thr"]))
     _pp_check(got, {k: g["c%d_hais_%s" % (ci, k)] for k in ("label_id", "conf", "bbox", "mask_offsets", "mask_points")})
+    from helpers import sg_mask_scores
+    import torch
+    dd = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    sgm = sg_mask_scores(int(c["sg_seed"]), np.asarray(c["proposals_idx"]).shape[0])
+    got_sg = postprocess.softgroup_pred_instances(xyz, pidx, xyz.size(0), dd(c["sg_cls_scores"]), dd(c["sg_iou_scores"]),
+                                                  dd(sgm), int(c["instance_classes"]), float(c["mask_thr"]),
+                                                  float(c["cls_thr"]), int(c["npoint_thr"]))
+    _pp_check(got_sg, {k: g["c%d_sg_%s" % (ci, k)] for k in ("label_id", "conf", "bbox", "mask_offsets", "mask_points")})
     # the reference's list-of-dicts format incl. RLE strings round-trips to the same masks
     ref_fmt = postprocess.to_reference_format(got, "scene0000_00", int(np.asarray(c["xyz"]).shape[0]))
     assert len(ref_fmt) == got["label_id"].numel()
