@@ -140,12 +140,7 @@ class CoordinateManager:
                     key = CoordinateMapKey(s)
                     if key not in self._maps:
                         self._maps[key] = _CoordMap(oc, table, s)
-            elif self._size_hints is not None and new_stride in self._size_hints:
-                m = self._size_hints[new_stride]
-                table, _, _, out_coords, d_count = ops.coord_unique_async(src.coords, new_stride)
-                ops.defer_count_check(d_count, m, "coordinate map of tensor stride %d (size hint)" % new_stride)
-                self._maps[out_key] = _CoordMap(out_coords[:m], table, new_stride)
-            else:
+            else:  # small tensors: one level at a time, one host read each (size hints are used by the pyramid only)
                 table, _, _, out_coords = ops.coord_unique(src.coords, quant=new_stride)
                 self._maps[out_key] = _CoordMap(out_coords, table, new_stride)
         return out_key
