@@ -365,3 +365,43 @@ def test_postproc_oracle_matches_reference_methods(ci):
                                            int(c["npoint_thr"]))
     _check_instances(sg, g, "c%d_sg_" % ci)
     assert sg["label_id"].size > 0
+
+
+# ------------------------------------------------------------------------------------------
+# checkpoint compatibility pinned by the reference's own module classes
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["pointgroup", "hais", "softgroup"])
+def test_state_dict_names_and_shapes_equal_reference_classes(name):
+    """tests/golden/reference_state_dicts.json = state_dict() of the reference's PointGroup / HAIS / SoftGroup
+    (instantiated from /root/reference by tests/golden/make_state_dict_golden.py)."""
+    import json
+    from minsu3d_b200.harness import models
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_state_dicts.json")) as f:
+        want = json.load(f)[name]
+    model = models.build_model(models.Config.for_model(name))
+    got = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert set(got) == set(want)
+    assert got == want
+
+
+def test_load_reference_checkpoint_roundtrip_and_errors(tmp_path):
+    from minsu3d_b200.harness import checkpoint, models
+    torch.manual_seed(0)
+    src = models.build_model(models.Config.for_model("pointgroup"))
+    path = str(tmp_path / "PointGroup_best.ckpt")
+    checkpoint.save_reference_checkpoint(src, path, epoch=3)
+    assert set(torch.load(path, weights_only=False)) >= {"state_dict", "epoch"}
+    torch.manual_seed(1)
+    dst = models.build_model(models.Config.for_model("pointgroup"))
+    assert checkpoint.load_reference_checkpoint(dst, path) == ([], [])
+    for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert torch.equal(a, b), k
+    with pytest.raises(ValueError, match="shape mismatches"):  # a HAIS (m=32) checkpoint does not fit PointGroup (m=16)
+        checkpoint.load_reference_checkpoint(dst, models.build_model(models.Config.for_model("hais")).state_dict())
+    sd = src.state_dict()
+    sd.pop("score_branch.weight")
+    with pytest.raises(ValueError, match="1 missing"):
+        checkpoint.load_reference_checkpoint(dst, {"state_dict": sd})
+    assert checkpoint.load_reference_checkpoint(dst, {"state_dict": sd}, strict=False) == (["score_branch.weight"], [])
+    with pytest.raises(ValueError, match="not a checkpoint"):
+        checkpoint.load_reference_checkpoint(dst, {"state_dict": 3})
