@@ -405,3 +405,21 @@ def test_load_reference_checkpoint_roundtrip_and_errors(tmp_path):
     assert checkpoint.load_reference_checkpoint(dst, {"state_dict": sd}, strict=False) == (["score_branch.weight"], [])
     with pytest.raises(ValueError, match="not a checkpoint"):
         checkpoint.load_reference_checkpoint(dst, {"state_dict": 3})
+
+
+def test_deferred_count_checks_host_logic():
+    """ops.defer_count_check / run_deferred_checks: claims are validated at the next host read; a wrong claim or a
+    range error raises and clears the list (host logic only: plain CPU tensors stand in for the device counts)."""
+    from minsu3d_b200 import ops
+    ops.run_deferred_checks()  # empty list: no-op
+    ops.defer_count_check(torch.tensor([10, 0], dtype=torch.int32), 10, "a")
+    ops.defer_count_check(torch.tensor([7, 0], dtype=torch.int32), 7, "b")
+    ops.run_deferred_checks()
+    ops.defer_count_check(torch.tensor([10, 0], dtype=torch.int32), 10, "ok")
+    ops.defer_count_check(torch.tensor([9, 0], dtype=torch.int32), 10, "level 4")
+    with pytest.raises(ValueError, match="level 4: claimed 10 rows but the device counted 9"):
+        ops.run_deferred_checks()
+    ops.run_deferred_checks()  # cleared by the failure
+    ops.defer_count_check(torch.tensor([5, 1], dtype=torch.int32), 5, "range")
+    with pytest.raises(ValueError, match="packable range"):
+        ops.run_deferred_checks()
