@@ -7,7 +7,7 @@
 // rows with similar neighbourhoods fixes that without touching the result: rows are sorted by
 //     key = [which of the six faces (-x,+x,-y,+y,-z,+z) of the 3^3 stencil hold any neighbour] : [27-bit mask]
 // and the convolution runs over the permuted table, storing row t of a tile at out[row_perm[t]].  On the
-// benchmark batch this leaves 12.7 active offsets per tile (scratch/tile_mask_probe2.py), i.e. 2.1x fewer
+// benchmark batch this leaves 12.7 active offsets per tile (tools/tile_mask_probe.py), i.e. 2.1x fewer
 // gather slabs and MMAs.  The output is the same sum in the same k order (skipped terms are exact zeros).
 #include <cub/device/device_radix_sort.cuh>
 
