@@ -423,3 +423,46 @@ def test_deferred_count_checks_host_logic():
     ops.defer_count_check(torch.tensor([5, 1], dtype=torch.int32), 5, "range")
     with pytest.raises(ValueError, match="packable range"):
         ops.run_deferred_checks()
+
+
+def test_tile_order_restatement_properties():
+    """oracle.tile_order (what tests/test_gpu_maps_conv.py checks the CUDA schedule against): a stable permutation
+    grouped by (stencil faces, neighbour mask); tile masks are the OR of their rows; far fewer active offsets."""
+    rng = np.random.default_rng(4)
+    c = surface_voxels(rng, 20_000, batch=2)
+    nbr = oracle.kernel_map(c, c, 3, 1)
+    perm, nbr_sorted, tile_mask = oracle.tile_order(nbr)
+    n = nbr.shape[0]
+    assert np.array_equal(np.sort(perm), np.arange(n)) and np.array_equal(nbr_sorted, nbr[perm])
+    masks = ((nbr_sorted >= 0).astype(np.int64) << np.arange(27)).sum(1)
+    change = np.nonzero(masks[1:] != masks[:-1])[0] + 1
+    for a, b in zip(np.concatenate(([0], change)), np.concatenate((change, [n]))):
+        assert np.all(np.diff(perm[a:b]) > 0)  # stable: equal keys keep first-occurrence order
+    assert len(np.unique(masks)) == len(change) + 1  # every mask forms one contiguous run
+    for t in (0, len(tile_mask) // 2, len(tile_mask) - 1):
+        want = np.bitwise_or.reduce(masks[t * 128:(t + 1) * 128])
+        assert int(tile_mask[t]) == int(want)
+    popc = lambda ms: np.mean([bin(int(m)).count("1") for m in ms])
+    shuffled = ((nbr >= 0).reshape(-1, 27)[rng.permutation(n)][:n // 128 * 128].reshape(-1, 128, 27).any(1)).sum(1).mean()
+    assert popc(tile_mask) < 0.6 * shuffled
+
+
+def test_postproc_restatement_edge_cases():
+    from oracle import postproc
+    n = 50
+    xyz = np.arange(n * 3, dtype=np.float32).reshape(n, 3)
+    sem = np.full(n, 5)
+    # two identical proposals (IoU 1) with tied scores, a disjoint one, duplicated pairs inside proposal 0
+    p0 = np.arange(0, 20)
+    pidx = np.concatenate([np.stack((np.full(20, 0), p0), 1), np.stack((np.full(5, 0), p0[:5]), 1),
+                           np.stack((np.full(20, 1), p0), 1), np.stack((np.full(15, 2), np.arange(30, 45)), 1)]).astype(np.int32)
+    scores = np.array([[1.0], [1.0], [0.5]], np.float32)
+    out = postproc.pointgroup_pred_instances(xyz, scores, pidx, 3, sem, 2, 0.09, 10, 0.3)
+    assert out["proposal"].tolist() == [0, 2]  # tie: the lower proposal wins, its twin is suppressed
+    assert out["mask_offsets"].tolist() == [0, 20, 35]  # duplicated pairs count once (the dense mask is a set)
+    assert out["label_id"].tolist() == [4, 4] and np.array_equal(out["bbox"][1], np.concatenate((xyz[30], xyz[44])))
+    assert np.array_equal(postproc.nms(np.eye(3, dtype=np.float32), np.array([0.1, 0.9, 0.5], np.float32), 0.3), [1, 2, 0])
+    empty = postproc.pointgroup_pred_instances(xyz, scores, pidx, 3, sem, 2, 0.09, 100, 0.3)
+    assert empty["label_id"].size == 0 and empty["mask_offsets"].tolist() == [0] and empty["bbox"].shape == (0, 6)
+    hs = postproc.hais_pred_instances(xyz, scores, pidx, 3, np.ones((pidx.shape[0], 1), np.float32), sem, 2, -0.5, 0.09, 15)
+    assert hs["proposal"].tolist() == [0, 1, 2]  # no NMS in HAIS, >= on the point count
