@@ -18,6 +18,8 @@ SOURCES = ["hash_map.cu", "tile_order.cu", "conv_simt.cu", "conv_tc.cu", "conv_a
            "cluster.cu", "segops.cu", "postproc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "177"]
+# experiment switches of individual kernels (e.g. "-DB2S_TC_MIN_CTAS=4"); part of the build stamp
+NVCC_FLAGS += os.environ.get("B2S_NVCC_EXTRA", "").split()
 
 
 def _digest():

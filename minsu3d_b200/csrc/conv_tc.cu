@@ -28,6 +28,19 @@
 
 namespace b2s {
 
+// Round-2 experiment switches (compile time, `B2S_NVCC_EXTRA="-DB2S_TC_MIN_CTAS=4 -DB2S_TC_IDX_AHEAD=1" python
+// minsu3d_b200/csrc/build.py --force`); the defaults reproduce the measured round-1 kernel exactly.
+//   B2S_TC_MIN_CTAS : CTAs per SM the register allocation aims for (4 -> 80 registers, 64-80 B of spills; combine with
+//                     B2S_TC_SB=16 at run time so that four weight rings fit the shared memory)
+//   B2S_TC_IDX_AHEAD: producers read the NEXT offset's gather index from shared memory one slab ahead of its use
+//                     (profiles/r01_conv_tc_sorted_stalls.txt: 11 % of the samples wait on that LDS)
+#ifndef B2S_TC_MIN_CTAS
+#define B2S_TC_MIN_CTAS 3
+#endif
+#ifndef B2S_TC_IDX_AHEAD
+#define B2S_TC_IDX_AHEAD 0
+#endif
+
 constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 192;  // warps 0-3: gather producers + epilogue, warp 4: MMA issuer, warp 5: weight loader
 constexpr int TC_A_SLAB = TC_BM * 64;  // bytes
@@ -187,7 +200,7 @@ struct TcArgs {
 };
 
 template <bool PAIRS, int NSPLIT>
-__global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, B2S_TC_MIN_CTAS) conv_tc_kernel(const TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -360,12 +373,23 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const TcArgs a) 
     uint32_t km = kmask;
     int lk = 0, lc = 0;  // kernel offset / channel chunk of the NEXT slab to load
     float ra[16], rb[16], rc[16];
+#if B2S_TC_IDX_AHEAD
+    int g_cur = -1;
+    int g_ahead = my_idx[PAIRS ? 0 : max(__ffs(km) - 1, 0)];  // index of the first offset
+#endif
     auto load_next = [&](float (&dst)[16]) {
       const bool adv = (lc == 0);
       const int kn = __ffs(km) - 1;
       lk = adv ? kn : lk;
       km = adv ? (km & (km - 1)) : km;
+#if B2S_TC_IDX_AHEAD
+      g_cur = adv ? g_ahead : g_cur;
+      const int g = g_cur;
+      // the index of the offset after this one, read one slab ahead of its use
+      g_ahead = my_idx[PAIRS ? 0 : max(__ffs(km) - 1, 0)];
+#else
       const int g = my_idx[PAIRS ? 0 : lk];
+#endif
       const float* p = (g >= 0) ? Ag + ((int64_t)g * c_in + lc * 16) : g_zero_row;
       // two 256-bit loads (LDG.E.256, sm_100) per slab and thread
       asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
