@@ -195,6 +195,24 @@ int b2s_resblock_backward(const float* gout, const float* x, const float* y1, co
                           float* tmp_a, float* tmp_b, float* tmp_c,
                           int32_t* bn_counter, int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream);
 
+/* BN -> ReLU -> strided convolution (mode 0, common.py:67-69) or transposed convolution (mode 1, common.py:75-77)
+ * of a U-Net level as one call; the strided map fine -> coarse is passed as its table nbr[n_coarse, K] and its
+ * pair lists (pair_in = fine row, pair_out = coarse row).  x has n_fine rows in mode 0 and n_coarse rows in mode 1.
+ * Saves y = relu(bn(x)) and stats [2,c_in] = (mean, rstd); backward needs tmp [n_x, c_in] scratch, dgb [2,c_in].
+ * Experimental in round 1: not yet exercised on a GPU, the harness keeps it switched off.                       */
+int b2s_bnconv_forward(const float* x, int64_t n_x, int32_t c_in, int32_t c_out, const float* gamma, const float* beta,
+                       float* rmean, float* rvar, float eps, float mom, const float* W, int32_t mode,
+                       const int32_t* nbr, const uint32_t* tile_mask, const int32_t* pair_in, const int32_t* pair_out,
+                       const int32_t* k_offsets, int64_t max_pairs, int64_t n_coarse, int64_t n_fine, int32_t K,
+                       float* y, float* stats, float* out, int32_t* bn_counter, int32_t algo, void* ws, size_t ws_bytes,
+                       b2s_stream_t stream);
+int b2s_bnconv_backward(const float* gout, const float* x, const float* y, const float* stats, const float* gamma,
+                        const float* W, int64_t n_x, int32_t c_in, int32_t c_out, int32_t mode, const int32_t* nbr,
+                        const uint32_t* tile_mask, const int32_t* pair_in, const int32_t* pair_out,
+                        const int32_t* k_offsets, int64_t max_pairs, int64_t n_coarse, int64_t n_fine, int32_t K,
+                        float* gx, float* gW, float* dgb, float* tmp, int32_t* bn_counter, int32_t algo, void* ws,
+                        size_t ws_bytes, b2s_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * V2 -- devoxelise gather and its scatter-add gradient (backbone.py:40, pointgroup.py:88).
  * idx is int64 (voxel_point_map dtype, data_module.py:65).

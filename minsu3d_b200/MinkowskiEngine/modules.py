@@ -508,3 +508,81 @@ def fused_residual_block(x, bn1, conv1, bn2, conv2, downsample=None):
     out = _ResBlockFn.apply(x.F, b1.weight, b1.bias, conv1.kernel, b2.weight, b2.bias, conv2.kernel,
                             None if downsample is None else downsample.kernel, b1, b2, kmap)
     return SparseTensor(out, coordinate_map_key=key, coordinate_manager=mgr)
+
+
+class _BnReluConvFn(torch.autograd.Function):
+    """relu(bn(x)) -> strided convolution (mode 0) / transposed convolution (mode 1) of a U-Net level in one call
+    (csrc/fused.cu: b2s_bnconv_forward/backward).  EXPERIMENTAL: not yet exercised on a GPU."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, kernel, bn, kmap, mode):
+        x = x.contiguous()
+        n_x, cin = x.shape
+        K, _, cout = kernel.shape
+        dev = x.device
+        n_out = kmap.n_out if mode == 0 else kmap.n_in
+        saved = torch.empty(n_x * cin + 2 * cin, dtype=torch.float32, device=dev)  # y | stats
+        out = torch.empty((n_out, cout), dtype=torch.float32, device=dev)
+        p_y = saved.data_ptr()
+        p_s = p_y + 4 * n_x * cin
+        pin, pout, koff, maxp = kmap.pairs()
+        algo = ops.get_conv_algo()
+        c = max(cin, cout)
+        ws = ops.workspace(ops.resblock_ws_bytes(K, c, c), dev)
+        ops.check(ops.lib().b2s_bnconv_forward(
+            x.data_ptr(), n_x, cin, cout, gamma.data_ptr(), beta.data_ptr(), ops.ptr(bn.running_mean),
+            ops.ptr(bn.running_var), bn.eps, bn.momentum if bn.running_mean is not None else 0.0, kernel.data_ptr(),
+            int(mode), kmap.nbr.data_ptr(), ops.ptr(kmap.tile_mask), pin.data_ptr(), pout.data_ptr(), koff.data_ptr(),
+            int(maxp), kmap.n_out, kmap.n_in, K, p_y, p_s, out.data_ptr(), ops.bn_counter(dev).data_ptr(), algo,
+            ws.data_ptr(), ws.numel(), ops.stream()), "bnconv_forward")
+        ctx.save_for_backward(x, saved, gamma, kernel)
+        ctx.kmap, ctx.mode, ctx.algo = kmap, int(mode), algo
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, saved, gamma, kernel = ctx.saved_tensors
+        kmap, mode = ctx.kmap, ctx.mode
+        gout = gout.contiguous()
+        n_x, cin = x.shape
+        K, _, cout = kernel.shape
+        dev = x.device
+        p_y = saved.data_ptr()
+        p_s = p_y + 4 * n_x * cin
+        gx = torch.empty_like(x)
+        gw = torch.empty_like(kernel)
+        dgb = torch.empty((2, cin), dtype=torch.float32, device=dev)
+        tmp = torch.empty((n_x, cin), dtype=torch.float32, device=dev)
+        pin, pout, koff, maxp = kmap.pairs()
+        c = max(cin, cout)
+        ws = ops.workspace(ops.resblock_ws_bytes(K, c, c), dev)
+        ops.check(ops.lib().b2s_bnconv_backward(
+            gout.data_ptr(), x.data_ptr(), p_y, p_s, gamma.data_ptr(), kernel.data_ptr(), n_x, cin, cout, mode,
+            kmap.nbr.data_ptr(), ops.ptr(kmap.tile_mask), pin.data_ptr(), pout.data_ptr(), koff.data_ptr(), int(maxp),
+            kmap.n_out, kmap.n_in, K, gx.data_ptr(), gw.data_ptr(), dgb.data_ptr(), tmp.data_ptr(),
+            ops.bn_counter(dev).data_ptr(), ctx.algo, ws.data_ptr(), ws.numel(), ops.stream()), "bnconv_backward")
+        return gx, dgb[0], dgb[1], gw, None, None, None
+
+
+def bn_relu_conv_fusable(x, bn_mod, conv):
+    b = bn_mod.bn
+    return (b.training and b.affine and b.track_running_stats and b.momentum is not None and conv.bias is None
+            and conv.kernel_size == 2 and conv.stride == 2 and conv.in_channels % 4 == 0 and conv.out_channels % 4 == 0
+            and x.F.is_cuda and x.F.size(0) > 0 and torch.is_grad_enabled())
+
+
+def fused_bn_relu_conv(x, bn_mod, conv):
+    """BN -> ReLU -> MinkowskiConvolution(k=2,s=2) or MinkowskiConvolutionTranspose(k=2,s=2) (common.py:67-77)."""
+    mgr, key = x.coordinate_manager, x.coordinate_map_key
+    b = bn_mod.bn
+    if conv.is_transpose:
+        out_key = mgr.existing_key(key.stride // conv.stride)
+        kmap = mgr.kernel_map(out_key, key, conv.kernel_size)  # the forward strided map (fine -> coarse)
+        mode = 1
+    else:
+        out_key = mgr.stride_key(key, conv.stride)
+        kmap = mgr.kernel_map(key, out_key, conv.kernel_size)
+        mode = 0
+    b.num_batches_tracked += 1
+    out = _BnReluConvFn.apply(x.F, b.weight, b.bias, conv.kernel, b, kmap, mode)
+    return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)

@@ -157,4 +157,73 @@ int b2s_resblock_backward(const float* gout, const float* x, const float* y1, co
   return add_inplace(gx, gout, n, c_in, stream);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// BN -> ReLU -> strided convolution (mode 0, common.py:67-69) / transposed convolution (mode 1, common.py:75-77) of a
+// U-Net level as one call.  The strided map fine -> coarse is given as its table nbr[n_coarse, K] and its pair lists
+// (pair_in = fine row, pair_out = coarse row).  Same kernels and operands as the module-by-module path.
+// NOT yet run on a GPU (written after the round-1 GPU budget was spent): the harness keeps it switched off
+// (harness/models.py: FUSED_UPDOWN) until tools/experiments/fused_updown_check.py has passed.
+// ---------------------------------------------------------------------------------------------------------------
+int b2s_bnconv_forward(const float* x, int64_t n_x, int32_t c_in, int32_t c_out, const float* gamma, const float* beta,
+                       float* rmean, float* rvar, float eps, float mom, const float* W, int32_t mode,
+                       const int32_t* nbr, const uint32_t* tile_mask, const int32_t* pair_in, const int32_t* pair_out,
+                       const int32_t* k_offsets, int64_t max_pairs, int64_t n_coarse, int64_t n_fine, int32_t K,
+                       float* y, float* stats, float* out, int32_t* bn_counter, int32_t algo, void* ws, size_t ws_bytes,
+                       b2s_stream_t stream) {
+  if (n_x < 0 || c_in < 4 || c_out < 4 || (c_in & 3) || (c_out & 3) || (mode != 0 && mode != 1) ||
+      n_x != (mode == 0 ? n_fine : n_coarse) || (mode == 0 && !nbr) || (mode == 1 && (!pair_in || !pair_out || !k_offsets))) {
+    set_error("bnconv_forward: invalid argument");
+    return B2S_E_INVALID;
+  }
+  if (n_x == 0) return B2S_OK;
+  Workspace w(ws, ws_bytes);
+  const size_t bn_bytes = b2s_bn_ws_bytes(n_x, c_in);
+  char* bn_ws = w.take<char>(bn_bytes);
+  if (!bn_ws) {
+    set_error("bnconv_forward: workspace too small");
+    return B2S_E_WORKSPACE;
+  }
+  char* conv_ws = (char*)ws + w.off;
+  const size_t conv_bytes = ws_bytes - w.off;
+  B2S_TRY(b2s_bn_forward(x, n_x, c_in, eps, mom, rmean, rvar, gamma, beta, 1, y, stats, stats + c_in, bn_counter, bn_ws,
+                         bn_bytes, stream));
+  if (mode == 0)
+    return b2s_conv_table(y, W, nbr, tile_mask, out, n_coarse, K, c_in, c_out, 0, 0, algo, conv_ws, conv_bytes, stream);
+  return b2s_conv_pairs(y, W, pair_out, pair_in, k_offsets, out, K, c_in, c_out, 0, max_pairs, algo, conv_ws, conv_bytes,
+                        stream);
+}
+
+int b2s_bnconv_backward(const float* gout, const float* x, const float* y, const float* stats, const float* gamma,
+                        const float* W, int64_t n_x, int32_t c_in, int32_t c_out, int32_t mode, const int32_t* nbr,
+                        const uint32_t* tile_mask, const int32_t* pair_in, const int32_t* pair_out,
+                        const int32_t* k_offsets, int64_t max_pairs, int64_t n_coarse, int64_t n_fine, int32_t K,
+                        float* gx, float* gW, float* dgb, float* tmp, int32_t* bn_counter, int32_t algo, void* ws,
+                        size_t ws_bytes, b2s_stream_t stream) {
+  if (n_x < 0 || c_in < 4 || c_out < 4 || (c_in & 3) || (c_out & 3) || (mode != 0 && mode != 1) ||
+      n_x != (mode == 0 ? n_fine : n_coarse) || !pair_in || !pair_out || !k_offsets || (mode == 1 && !nbr)) {
+    set_error("bnconv_backward: invalid argument");
+    return B2S_E_INVALID;
+  }
+  Workspace w(ws, ws_bytes);
+  const size_t bn_bytes = b2s_bn_ws_bytes(n_x, c_in);
+  char* bn_ws = w.take<char>(bn_bytes);
+  if (!bn_ws) {
+    set_error("bnconv_backward: workspace too small");
+    return B2S_E_WORKSPACE;
+  }
+  char* conv_ws = (char*)ws + w.off;
+  const size_t conv_bytes = ws_bytes - w.off;
+  if (mode == 0) {
+    // every fine row has exactly one (coarse row, offset): plain stores, no accumulation
+    B2S_TRY(b2s_conv_pairs(gout, W, pair_out, pair_in, k_offsets, tmp, K, c_out, c_in, 1, max_pairs, algo, conv_ws,
+                           conv_bytes, stream));
+    B2S_TRY(b2s_conv_wgrad(y, gout, pair_in, pair_out, k_offsets, gW, K, c_in, c_out, max_pairs, algo, stream));
+  } else {
+    B2S_TRY(b2s_conv_table(gout, W, nbr, tile_mask, tmp, n_coarse, K, c_out, c_in, 1, 0, algo, conv_ws, conv_bytes, stream));
+    B2S_TRY(b2s_conv_wgrad(y, gout, pair_out, pair_in, k_offsets, gW, K, c_in, c_out, max_pairs, algo, stream));
+  }
+  return b2s_bn_backward(x, y, tmp, n_x, c_in, stats, stats + c_in, gamma, 1, 1, gx, dgb, dgb + c_in, bn_counter, bn_ws,
+                         bn_bytes, stream);
+}
+
 }  // extern "C"

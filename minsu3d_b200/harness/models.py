@@ -26,6 +26,7 @@ from . import scenes
 # MinkUNet pieces (common.py:21-95, backbone.py:8-43, tiny_unet.py:7-19)
 # ------------------------------------------------------------------------------------------
 ASYNC_SIZES = True   # use the loader's level sizes / uniqueness guarantees instead of host reads (validated on device)
+FUSED_UPDOWN = False  # BN->ReLU->(de)conv of the U-Net levels as one call: written, NOT yet run on a GPU (round 2)
 FUSED_BLOCKS = True  # training-mode residual blocks through b2s_resblock_forward/backward (host-side fusion)
 
 
@@ -75,11 +76,17 @@ class UBlock(nn.Module):
             self.blocks_tail = nn.Sequential(OrderedDict(
                 ("block%d" % i, block(c * (2 - i), c, 3, norm_fn)) for i in range(block_reps)))
 
+    @staticmethod
+    def _bn_relu_conv(seq, x):
+        if FUSED_UPDOWN and me_modules.bn_relu_conv_fusable(x, seq[0], seq[2]):
+            return me_modules.fused_bn_relu_conv(x, seq[0], seq[2])
+        return seq(x)
+
     def forward(self, x):
         out = self.blocks(x)
         if len(self.nPlanes) > 1:
             skip = out
-            out = self.deconv(self.u(self.conv(out)))
+            out = self._bn_relu_conv(self.deconv, self.u(self._bn_relu_conv(self.conv, out)))
             out = self.blocks_tail(ME.cat(skip, out))
         return out
 
