@@ -173,6 +173,38 @@ def test_me_oracle_transposed_conv_is_adjoint_structure_of_strided_conv():
     assert np.abs(got - want).max() < 1e-4
 
 
+def test_me_oracle_strided_and_transposed_conv_equal_dense_torch():
+    """2^3 / stride-2 convolution and its transposed form vs dense torch conv3d(stride=2) / conv_transpose3d(stride=2):
+    pins the even-kernel offset enumeration (not centred, x fastest, appendix A.4-6) independently of me_ref."""
+    rng = np.random.default_rng(12)
+    c = random_voxels(rng, 1200, extent=10, batch=2)
+    c[:, 1:] = np.abs(c[:, 1:]) % 8
+    c = oracle.coord_unique(c, 1)[2]
+    _, _, oc = oracle.coord_unique(c, 2)
+    n, m, cin, cout = c.shape[0], oc.shape[0], 5, 6
+    nbr = oracle.kernel_map(c, oc, 2, 1)
+    x = rng.standard_normal((n, cin)).astype(np.float32)
+    w = rng.standard_normal((8, cin, cout)).astype(np.float32)
+    ct, ot = torch.from_numpy(c).long(), torch.from_numpy(oc).long()
+    dense = torch.zeros(2, cin, 8, 8, 8, dtype=torch.float64)
+    dense[ct[:, 0], :, ct[:, 3], ct[:, 2], ct[:, 1]] = torch.from_numpy(x).double()
+    wd = torch.from_numpy(w).double().view(2, 2, 2, cin, cout).permute(4, 3, 0, 1, 2)  # [cout, cin, iz, iy, ix]
+    down = torch.nn.functional.conv3d(dense, wd, stride=2)
+    want = down[ot[:, 0], :, ot[:, 3] // 2, ot[:, 2] // 2, ot[:, 1] // 2].numpy()
+    got = oracle.conv_fwd(x, w, nbr, m)
+    assert np.abs(got - want).max() < 1e-4
+    # transposed: coarse [m, cout] -> fine [n, cin] with kernel (8, cout, cin); every fine voxel gets one term
+    xc = rng.standard_normal((m, cout)).astype(np.float32)
+    wt = rng.standard_normal((8, cout, cin)).astype(np.float32)
+    dense_c = torch.zeros(2, cout, 4, 4, 4, dtype=torch.float64)
+    dense_c[ot[:, 0], :, ot[:, 3] // 2, ot[:, 2] // 2, ot[:, 1] // 2] = torch.from_numpy(xc).double()
+    wtd = torch.from_numpy(wt).double().view(2, 2, 2, cout, cin).permute(3, 4, 0, 1, 2)  # [in=cout, out=cin, iz, iy, ix]
+    up = torch.nn.functional.conv_transpose3d(dense_c, wtd, stride=2)
+    want_up = up[ct[:, 0], :, ct[:, 3], ct[:, 2], ct[:, 1]].numpy()
+    got_up = oracle.convT_fwd(xc, wt, nbr, n)
+    assert np.abs(got_up - want_up).max() < 1e-4
+
+
 def test_oracle_backbone_forward_shapes_and_determinism():
     from minsu3d_b200.harness import models, scenes
     torch.manual_seed(123)
