@@ -108,3 +108,65 @@ def get_mask_label(proposals_idx, proposals_offset, instance_ids, instance_cls, 
         ops.get_mask_label(proposals_idx, proposals_offset, instance_ids, instance_cls, proposals_iou, n_inst,
                            n_prop, ignored_label, iou_thr, mask_label, mask_label_mask)
         return mask_label, mask_label_mask
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# voxelization_idx / voxelization: the names BASELINE.json's north_star uses for rows V1 / V2 of SURVEY.md 8(a).
+# They do not exist in the reference (minsu3d replaced the upstream PointGroup ops by
+# ME.utils.sparse_quantize(return_index, return_inverse), general_dataset.py:159-163 / general_model.py:187-189, and a
+# plain gather features[v2p_map], backbone.py:40), so they are thin aliases with exactly those semantics.
+# ---------------------------------------------------------------------------------------------------------------
+def voxelization_idx(coords, batchsize=None, mode=4):
+    """coords [N, 4] integer (batch, x, y, z) on the GPU -> (voxel_coords [M, 4] int32, p2v_map [N] int64,
+    v2p_map [M] int64): unique rows in first-occurrence order (the libb2s coordinate hash, row V1).
+    p2v_map[i] = voxel of point i (ME's inverse map); v2p_map[v] = first point of voxel v (ME's unique map).
+    `batchsize` / `mode` are accepted for signature compatibility with the upstream op and not needed."""
+    if not coords.is_cuda:
+        raise ValueError("voxelization_idx needs CUDA coordinates (libb2s has no CPU path)")
+    c = coords.to(torch.int32).contiguous()
+    _, unique_idx, inverse, out_coords = ops.coord_unique(c, 1)
+    return out_coords, inverse.long(), unique_idx.long()
+
+
+class Voxelization(Function):
+    """feats [N, C] -> voxel feats [M, C].  mode 4 = mean over the points of a voxel (upstream PointGroup default;
+    scatter-add with vector atomics + count), any other mode = first point of the voxel (what ME's
+    RANDOM_SUBSAMPLE quantisation, the reference's actual behaviour, keeps)."""
+
+    @staticmethod
+    def forward(ctx, feats, p2v_map, n_voxels, mode=4, v2p_map=None):
+        feats = feats.contiguous()
+        p2v_map = p2v_map.long().contiguous()
+        ctx.mode = int(mode)
+        if ctx.mode == 4:
+            out = torch.zeros((n_voxels, feats.size(1)), dtype=torch.float32, device=feats.device)
+            ops.check(ops.lib().b2s_scatter_add_rows(ops.ptr(feats), ops.ptr(p2v_map), feats.size(0), feats.size(1),
+                                                     ops.ptr(out), ops.stream()), "scatter_add_rows")
+            count = torch.bincount(p2v_map, minlength=n_voxels).clamp_(min=1).to(torch.float32)
+            ctx.save_for_backward(p2v_map, count)
+            return out / count[:, None]
+        if v2p_map is None:
+            raise ValueError("voxelization(mode != 4) needs v2p_map (first point of every voxel)")
+        ctx.save_for_backward(v2p_map.long().contiguous())
+        ctx.n = feats.size(0)
+        return ops.devoxelize(feats, v2p_map.long().contiguous())
+
+    @staticmethod
+    def backward(ctx, grad):
+        grad = grad.contiguous()
+        if ctx.mode == 4:
+            p2v_map, count = ctx.saved_tensors
+            return ops.devoxelize(grad / count[:, None], p2v_map), None, None, None, None
+        (v2p_map,) = ctx.saved_tensors
+        g = torch.zeros((ctx.n, grad.size(1)), dtype=torch.float32, device=grad.device)
+        ops.check(ops.lib().b2s_scatter_add_rows(ops.ptr(grad), ops.ptr(v2p_map), grad.size(0), grad.size(1),
+                                                 ops.ptr(g), ops.stream()), "scatter_add_rows")
+        return g, None, None, None, None
+
+
+voxelization = Voxelization.apply
+
+
+def devoxelization(voxel_feats, p2v_map):
+    """voxel feats [M, C] -> point feats [N, C] = voxel_feats[p2v_map] (backbone.py:40), scatter-add gradient."""
+    return ops.devoxelize(voxel_feats.contiguous(), p2v_map.long().contiguous())

@@ -746,23 +746,22 @@ __global__ void __launch_bounds__(128)
 }
 
 static int coop_grid(const void* kernel, int threads, int64_t work_items) {
-  // device / occupancy queries cost ~40 us each: cache them per kernel (one process drives one GPU)
-  static const void* cached_kernel[4] = {nullptr, nullptr, nullptr, nullptr};
-  static int cached_blocks[4] = {0, 0, 0, 0};
+  // device / occupancy queries cost ~40 us each: cache them per (device, kernel)
+  static const void* cached_kernel[B2S_MAX_DEVICES][4] = {};
+  static int cached_blocks[B2S_MAX_DEVICES][4] = {};
+  const int dev = current_device();
   int max_blocks = 0;
   for (int i = 0; i < 4; ++i)
-    if (cached_kernel[i] == kernel) max_blocks = cached_blocks[i];
+    if (cached_kernel[dev][i] == kernel) max_blocks = cached_blocks[dev][i];
   if (max_blocks == 0) {
-    int dev = 0, sms = B2S_SM_COUNT, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
     if (per_sm < 1) per_sm = 1;
-    max_blocks = sms * std::min(per_sm, 2);
+    max_blocks = sm_count() * std::min(per_sm, 2);
     for (int i = 0; i < 4; ++i)
-      if (cached_kernel[i] == nullptr) {
-        cached_kernel[i] = kernel;
-        cached_blocks[i] = max_blocks;
+      if (cached_kernel[dev][i] == nullptr) {
+        cached_kernel[dev][i] = kernel;
+        cached_blocks[dev][i] = max_blocks;
         break;
       }
   }

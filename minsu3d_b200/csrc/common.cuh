@@ -5,11 +5,31 @@
 #include <stdio.h>
 #include "../../include/b2s.h"
 
-#define B2S_SM_COUNT 148
+#define B2S_MAX_DEVICES 64
 
 namespace b2s {
 
 void set_error(const char* msg);
+
+// current device ordinal (clamped to the per-device cache size)
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < B2S_MAX_DEVICES) ? dev : 0;
+}
+
+// SM count of the current device, queried once per device (148 on B200); used by the grid heuristics
+inline int sm_count() {
+  static int cached[B2S_MAX_DEVICES] = {0};
+  const int dev = current_device();
+  int v = cached[dev];
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached[dev] = v;
+  }
+  return v;
+}
+#define B2S_SM_COUNT (::b2s::sm_count())
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -602,10 +602,11 @@ static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream, int splits =
   const size_t fixed = 1024 /*align slack*/ + 8 * (2 * 8 + 2 * 64 + 1) + 16 + (size_t)(PAIRS ? 2 * TC_BM : TC_BM * a.K) * 4 + 64;
   size_t smem = (size_t)a.sb * b_slot + fixed;
   auto kern = conv_tc_kernel<PAIRS, NSPLIT>;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[B2S_MAX_DEVICES] = {0};  // the attribute is per device (and per kernel instantiation)
+  const int dev = current_device();
+  if (smem > configured[dev]) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
+    configured[dev] = smem;
   }
   a.splits = splits;
   kern<<<dim3((unsigned)grid_x, (unsigned)splits), TC_THREADS, smem, stream>>>(a);

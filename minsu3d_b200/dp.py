@@ -42,7 +42,32 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def _host_group(group):
+    """A process group that can reduce small CPU tensors: the data group itself when it is gloo, else a gloo side
+    group over the same ranks (created once per process; every rank constructs its GradBucketer, so the collective
+    `new_group` call is matched)."""
+    if not dist.is_initialized():
+        return None
+    if dist.get_backend(group) == "gloo":
+        return group
+    key = id(group)
+    g = _HOST_GROUPS.get(key)
+    if g is None:
+        ranks = dist.get_process_group_ranks(group) if group is not None else None
+        g = _HOST_GROUPS[key] = dist.new_group(ranks=ranks, backend="gloo")
+    return g
+
+
+_HOST_GROUPS = {}
+
+
 class GradBucketer:
+    """Parameters that received no gradient on ANY rank keep `p.grad = None` after `finish()` -- the optimizer then
+    skips them exactly as it does at world size 1 and as the reference's DDP(find_unused_parameters=True) does
+    (config/model/base.yaml:12-20): e.g. the ScoreNet in a step where no rank found a proposal.  Which parameters
+    are used is host knowledge on every rank (hooks fired / `p.grad is not None`), so the global OR is one tiny
+    bit-mask all-reduce on the gloo side group: no device read, the host does not wait for the backward."""
+
     def __init__(self, params, bucket_mb=8.0, group=None, overlap=True):
         self.group = group
         self.overlap = overlap
@@ -85,6 +110,10 @@ class GradBucketer:
         self._next = 0
         self._handles = []
         self._hooks = []
+        self._index = {p: i for i, p in enumerate(self.params)}
+        self._used = [False] * len(self.params)  # overlap mode: set by the hooks
+        self.host_group = _host_group(group)
+        self.last_unused = 0  # parameters left without a gradient by the last finish() (globally unused)
         if self.world > 1 and overlap:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -100,7 +129,11 @@ class GradBucketer:
             return
         for flat in self.flats:
             flat.zero_()
+        for plist, views in zip(self.buckets, self.views):
+            for p, v in zip(plist, views):
+                p.grad = v  # finish() may have set globally unused parameters to None
         self._ready = [0] * len(self.buckets)
+        self._used = [False] * len(self.params)
         self._next = 0
         self._handles = []
         self.launched_in_backward = 0
@@ -110,17 +143,31 @@ class GradBucketer:
 
     def _on_grad(self, p):
         bi = self.bucket_of[p]
+        self._used[self._index[p]] = True
         self._ready[bi] += 1
         while self._next < len(self.buckets) and self._ready[self._next] == len(self.buckets[self._next]):
             self._launch(self._next)
             self._next += 1
             self.launched_in_backward += 1
 
+    def _global_used(self, used_local):
+        """OR over ranks of the per-parameter 'received a gradient' flags (host-side, 63 flags per int64 word)."""
+        words = [0] * ((len(used_local) + 62) // 63)
+        for i, u in enumerate(used_local):
+            if u:
+                words[i // 63] |= 1 << (i % 63)
+        t = torch.tensor(words, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.BOR, group=self.host_group)
+        words = t.tolist()
+        return [bool((words[i // 63] >> (i % 63)) & 1) for i in range(len(used_local))]
+
     def finish(self):
         """Launch the remaining buckets in order, wait for all of them, and average."""
         if self.world == 1:
             return
         if not self.overlap:
+            used = self._global_used([p.grad is not None for p in self.params])
+            self.last_unused = used.count(False)
             for flat, plist, views in zip(self.flats, self.buckets, self.views):
                 dst = [v for p, v in zip(plist, views) if p.grad is not None]
                 src = [p.grad for p in plist if p.grad is not None]
@@ -134,16 +181,19 @@ class GradBucketer:
             torch._foreach_mul_(self.flats, 1.0 / self.world)
             for plist, views in zip(self.buckets, self.views):
                 for p, v in zip(plist, views):
-                    p.grad = v
+                    p.grad = v if used[self._index[p]] else None
             return
         while self._next < len(self.buckets):
             self._launch(self._next)
             self._next += 1
+        used = self._global_used(self._used)
+        self.last_unused = used.count(False)
         for h in self._handles:
             h.wait()
-        inv = 1.0 / self.world
-        for flat in self.flats:
-            flat.mul_(inv)
+        torch._foreach_mul_(self.flats, 1.0 / self.world)
+        for p in self.params:
+            if not used[self._index[p]]:
+                p.grad = None  # restored to the bucket view by zero_grad()
 
     def grad_bytes(self):
         return sum(p.numel() * p.element_size() for p in self.params)

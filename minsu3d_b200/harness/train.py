@@ -59,6 +59,11 @@ class Trainer:
         total, losses, _ = self.model.training_loss(data)
         total.backward()
         self.bucketer.finish()
+        # Size claims made in this forward (SparseTensor(coordinates_unique / level_sizes), ops.py) are validated on
+        # the device BEFORE the weights change: the fused Adam skips the update when the flag is set (the GradScaler
+        # `found_inf` mechanism), no host read; the ValueError is raised by the next ops.run_deferred_checks().
+        if self.device.type == "cuda":
+            self.optimizer.found_inf = ops.deferred_failure_flag(self.device)
         self.optimizer.step()
         self.last_losses = losses
         return total.detach()

@@ -63,7 +63,7 @@ _DEFERRED = []  # (d_count int32[2] = {m, range_error}, expected m, what)
 
 def defer_count_check(d_count, expected, what):
     _DEFERRED.append((d_count, int(expected), what))
-    if len(_DEFERRED) >= 256:  # nobody synchronised for a long time: do it now
+    if len(_DEFERRED) >= 64:  # nobody synchronised for a long time (a few backbone-only forwards): do it now
         run_deferred_checks()
 
 
@@ -79,6 +79,21 @@ def run_deferred_checks():
             raise ValueError(_RANGE_MSG)
         if m != expected:
             raise ValueError("%s: claimed %d rows but the device counted %d" % (what, expected, m))
+
+
+def deferred_failure_flag(device):
+    """float32 [1] device tensor: 1.0 iff any pending size claim is wrong -- computed on the device, NO host read.
+
+    For loops that update weights before the next host read (Trainer.step): hand it to the fused optimizer as
+    `found_inf`, which then skips the update on the device, so a wrong claim (rows sliced to a wrong count,
+    un-subsampled features) can never reach the weights; the ValueError itself is raised by the next
+    run_deferred_checks().  Returns None when nothing is pending."""
+    if not _DEFERRED:
+        return None
+    counts = torch.stack([d for d, _, _ in _DEFERRED])
+    expected = torch.tensor([e for _, e, _ in _DEFERRED], dtype=I32).to(device, non_blocking=True)
+    bad = (counts[:, 0] != expected) | (counts[:, 1] != 0)
+    return bad.any().to(torch.float32).reshape(1)
 
 
 def coord_unique(coords, quant=1, assume_unique=False):
@@ -530,9 +545,6 @@ def get_mask_label(proposals_idx, proposals_offset, instance_labels, instance_cl
                                    float(iou_thr), ptr(mask_label), ptr(mask_label_mask), stream()), "get_mask_label")
 
 
-__all__ = [n for n in dir() if not n.startswith("_")]
-
-
 # ------------------------------------------------------------------------------------------
 # clusters_voxelization up to `.int()` (general_model.py:152-182)
 # ------------------------------------------------------------------------------------------
@@ -555,3 +567,6 @@ def clusters_voxelize(clusters_idx, clusters_offset, coords, scale, spatial_shap
                                       s_total, n_cluster, ptr(coords), float(scale), int(spatial_shape), ptr(rand),
                                       ptr(out), ptr(params), stream()), "clusters_voxelize")
     return out
+
+
+__all__ = [n for n in dir() if not n.startswith("_")]

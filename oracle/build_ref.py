@@ -32,6 +32,7 @@ def ref_so_path():
 
 def build(force=False, verbose=True):
     so = ref_so_path()
+    stage_python(force=force, verbose=verbose)
     if os.path.exists(so) and not force:
         return so
     if not os.path.isdir(REF_SRC):
@@ -70,6 +71,50 @@ def build(force=False, verbose=True):
     if verbose:
         print("built", so)
     return so
+
+
+REF_ROOT = "/root/reference"
+PY_OUT = os.path.join(OUT, "refpy")
+
+
+def stage_python(force=False, verbose=True):
+    """Stage the reference's own Python for the hot path's callers -- minsu3d/model/**, minsu3d/common_ops/functions,
+    minsu3d/loss, minsu3d/evaluation, minsu3d/util and the model / data YAML configs -- under oracle/_ref/refpy/
+    (git-ignored OUTPUT directory, travels to the GPU box like the compiled reference COMMON_OPS; never committed).
+    tests/test_gpu_reference_forward.py imports it from there and runs the reference's unmodified PointGroup /
+    HAIS / SoftGroup `forward` + `_loss` on top of the drop-in (minsu3d_b200.install_as_reference_modules()).
+    Returns the staged root or None when neither the staged copy nor /root/reference exists."""
+    import shutil
+    marker = os.path.join(PY_OUT, "minsu3d", "model", "pointgroup.py")
+    if os.path.exists(marker) and not force:
+        return PY_OUT
+    src = os.path.join(REF_ROOT, "minsu3d")
+    if not os.path.isdir(src):
+        return None
+    if os.path.isdir(PY_OUT):
+        shutil.rmtree(PY_OUT)
+    for sub in ("model", "common_ops/functions", "loss", "evaluation", "util", "data"):
+        for root, _, files in os.walk(os.path.join(src, sub)):
+            rel = os.path.relpath(root, REF_ROOT)
+            for f in files:
+                if f.endswith(".py"):
+                    os.makedirs(os.path.join(PY_OUT, rel), exist_ok=True)
+                    shutil.copyfile(os.path.join(root, f), os.path.join(PY_OUT, rel, f))
+    for rel in ("minsu3d/__init__.py", "minsu3d/common_ops/__init__.py"):
+        dst = os.path.join(PY_OUT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if os.path.exists(os.path.join(REF_ROOT, rel)):
+            shutil.copyfile(os.path.join(REF_ROOT, rel), dst)
+        elif not os.path.exists(dst):
+            open(dst, "w").close()
+    for sub in ("config/model", "config/data"):
+        os.makedirs(os.path.join(PY_OUT, sub), exist_ok=True)
+        for f in os.listdir(os.path.join(REF_ROOT, sub)):
+            if f.endswith(".yaml"):
+                shutil.copyfile(os.path.join(REF_ROOT, sub, f), os.path.join(PY_OUT, sub, f))
+    if verbose:
+        print("staged reference python under", PY_OUT)
+    return PY_OUT
 
 
 def load():

@@ -87,6 +87,52 @@ def test_bucketed_allreduce_world2_gloo(tmp_path, overlap):
         assert res[0]["launched_in_backward"] == 0  # pack-after-backward mode: collectives only in finish()
 
 
+def _adam_run(net, bucketer, x, pattern):
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+    unused = []
+    for use_extra in pattern:
+        bucketer.zero_grad()
+        net(x, use_extra=use_extra).backward()
+        bucketer.finish()
+        unused.append(sum(p.grad is None for p in net.parameters()))
+        opt.step()
+    return {n: p.detach().clone() for n, p in net.named_parameters()}, unused
+
+
+def _worker_unused(rank, world, port, result_dir, overlap):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dp.init_from_env(backend="gloo")
+    torch.manual_seed(0)
+    net = _Net()
+    bucketer = dp.GradBucketer(net.parameters(), bucket_mb=0.0005, overlap=overlap)
+    x = torch.randn(5, 8, generator=torch.Generator().manual_seed(7))  # same batch on both ranks: mean grad = grad
+    params, unused = _adam_run(net, bucketer, x, [True, False, False, True])
+    torch.save({"params": params, "unused": unused}, os.path.join(result_dir, "rank%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_globally_unused_parameters_are_skipped_like_world1(tmp_path, overlap):
+    """A head that gets no gradient on ANY rank (no proposals anywhere) must keep p.grad = None so that Adam skips
+    it -- no step-count advance, no stale-momentum update -- exactly as at world size 1 and as the reference's
+    DDP(find_unused_parameters=True) does."""
+    world, port = 2, _free_port()
+    mp.start_processes(_worker_unused, args=(world, port, str(tmp_path), overlap), nprocs=world, join=True,
+                       start_method="spawn")
+    res = [torch.load(os.path.join(tmp_path, "rank%d.pt" % r)) for r in range(world)]
+    torch.manual_seed(0)
+    net = _Net()
+    x = torch.randn(5, 8, generator=torch.Generator().manual_seed(7))
+    want, want_unused = _adam_run(net, dp.GradBucketer(net.parameters()), x, [True, False, False, True])
+    assert want_unused == [0, 2, 2, 0]
+    for r in range(world):
+        assert res[r]["unused"] == want_unused
+        for n, v in res[r]["params"].items():
+            assert torch.allclose(v, want[n], atol=1e-6), (r, n)
+
+
 def test_single_process_bucketer_is_a_noop_wrapper():
     net = _Net()
     b = dp.GradBucketer(net.parameters())

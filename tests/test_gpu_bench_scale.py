@@ -1,0 +1,123 @@
+"""Parity AT THE BENCHMARK CONFIGURATION (BASELINE.json configs[0]/[1]: 100k-point scenes at 2 cm voxels; the batch
+bench.py times is seeds 0..3): the MinkUNet backbone forward of the whole 4-scene batch, the full-backbone parameter
+gradients for m=16 (PointGroup) and m=32 (HAIS / SoftGroup), and the ball query + BFS clustering on the batch's
+~136k foreground points, all against the CPU oracle.  Tolerances are stated per path below.
+
+Oracle cost on the GPU box's host cores: forward ~1.5 s per 100k-point scene (m=16), gradients ~3x, ball query ~10 s
+per pass (brute force, like the reference)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import me_unet, me_unet_grad
+
+pytestmark = pytest.mark.gpu
+
+BENCH_SEEDS = [0, 1, 2, 3]
+N_POINTS = 100_000
+
+
+def _rel_max(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.abs(got - want).max() / max(np.abs(want).max(), 1e-12)
+
+
+def _rel_l2(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-12)
+
+
+@pytest.fixture(scope="module")
+def bench_batch():
+    from minsu3d_b200.harness import scenes
+    return scenes.make_batch(BENCH_SEEDS, "cuda", N_POINTS)
+
+
+def test_backbone_forward_on_the_bench_batch_matches_oracle(bench_batch):
+    """configs[1]'s backbone forward on the bench batch (4 x 100k points, ~325k voxels), tcgen05 3xTF32 path.
+    Tolerance 1e-4 relative to the output's max (north_star's fp32 tolerance)."""
+    from minsu3d_b200.harness import models
+    torch.manual_seed(123)
+    model = models.build_model(models.Config.for_model("pointgroup")).cuda().train()
+    out = model.backbone_forward(bench_batch)
+    assert bench_batch["voxel_xyz"].size(0) > 300_000
+    want = me_unet.backbone_forward(me_unet.numpy_state_dict(model), bench_batch["voxel_features"].cpu().numpy(),
+                                    bench_batch["voxel_xyz"].cpu().numpy(), bench_batch["voxel_point_map"].cpu().numpy())
+    for k in ("point_features", "semantic_scores", "point_offsets"):
+        err = _rel_max(out[k].detach().cpu().numpy(), want[k])
+        assert err < 1e-4, "%s rel err %.3e" % (k, err)
+
+
+@pytest.mark.parametrize("name", ["pointgroup", "hais"])
+def test_full_backbone_gradients_at_100k_points_match_oracle(name):
+    """Every backbone parameter gradient (7-level U-Net: 3^3 / strided / transposed / 1x1 convolutions, BatchNorms,
+    heads) of one 100k-point scene for m=16 (pointgroup) and m=32 (hais = softgroup backbone) against
+    oracle/me_unet_grad (orc_conv_bwd).  L = <semantic_scores, G1> + <point_offsets, G2> with fixed random G.
+    Tolerances: outputs 1e-4 of max; gradients 2e-3 relative L2 per parameter (the fp32 kernels and the float64-BN
+    oracle may disagree on the sign of the handful of ReLU pre-activations within rounding of zero, and the
+    weight-gradient atomics are order-nondeterministic at 1e-6), and 1e-3 on the concatenation of all gradients."""
+    from minsu3d_b200.harness import models, scenes
+    batch = scenes.make_batch([5], "cuda", N_POINTS)
+    torch.manual_seed(123)
+    model = models.build_model(models.Config.for_model(name)).cuda().train()
+    n = batch["point_xyz"].size(0)
+    rng = np.random.default_rng(1)
+    g_sem = rng.normal(size=(n, 20)).astype(np.float32)
+    g_off = rng.normal(size=(n, 3)).astype(np.float32)
+    out = model.backbone_forward(batch)
+    loss = (out["semantic_scores"] * torch.from_numpy(g_sem).cuda()).sum() + \
+           (out["point_offsets"] * torch.from_numpy(g_off).cuda()).sum()
+    loss.backward()
+    got = {k: p.grad.detach().cpu().numpy() for k, p in model.named_parameters() if p.grad is not None}
+    want_out, want = me_unet_grad.backbone_gradients(model, batch["voxel_features"].cpu().numpy(),
+                                                     batch["voxel_xyz"].cpu().numpy(),
+                                                     batch["voxel_point_map"].cpu().numpy(), g_sem, g_off)
+    for k in ("point_features", "semantic_scores", "point_offsets"):
+        err = _rel_max(out[k].detach().cpu().numpy(), want_out[k])
+        assert err < 1e-4, "%s rel err %.3e" % (k, err)
+    assert set(want) <= set(got) and len(want) > 150
+    worst = ("", 0.0)
+    for k, w in want.items():
+        if k.endswith("_branch.0.bias"):  # bias in front of a BatchNorm: exactly zero gradient
+            continue
+        err = _rel_l2(got[k], w)
+        worst = max(worst, (k, err), key=lambda t: t[1])
+        assert err < 2e-3, "%s: rel l2 %.3e" % (k, err)
+    keys = [k for k in want if not k.endswith("_branch.0.bias")]
+    allg = np.concatenate([got[k].ravel() for k in keys])
+    allw = np.concatenate([want[k].ravel() for k in keys])
+    assert _rel_l2(allg, allw) < 1e-3, "all gradients: %.3e (worst %s %.3e)" % (_rel_l2(allg, allw), *worst)
+    print("%s: %d gradients, worst %s %.2e, all %.2e" % (name, len(keys), worst[0], worst[1], _rel_l2(allg, allw)))
+
+
+def test_ballquery_and_bfs_on_the_bench_foreground_points_match_oracle(bench_batch):
+    """The clustering stage of configs[1] on the bench batch: ~136k foreground points, raw coordinates
+    (~1.2 M pairs) and shifted coordinates (~55 M pairs, many lists at the 1000 cap): ball-query lists and the BFS
+    clusters (membership AND visit order) bit-exact against the oracle."""
+    from minsu3d_b200 import ops
+    from minsu3d_b200.common_ops.functions import pointgroup_ops
+    from minsu3d_b200.harness import models
+    cfg = models.Config.for_model("pointgroup", proposal_source="gt_noise")
+    model = models.build_model(cfg).cuda()
+    scores, offsets = model._cluster_inputs(bench_batch, {"semantic_scores": torch.zeros(
+        (bench_batch["point_xyz"].size(0), cfg.classes), device="cuda")})
+    preds = scores.argmax(1).to(torch.int16)
+    obj = model._object_points(preds)
+    assert obj.numel() > 100_000
+    bidx = bench_batch["vert_batch_ids"][obj].contiguous()
+    offs = torch.cumsum(torch.bincount(bidx + 1), dim=0).int()
+    lab = preds[obj].contiguous()
+    raw = bench_batch["point_xyz"][obj].contiguous()
+    shifted = (bench_batch["point_xyz"] + offsets)[obj].contiguous()
+    for pts, min_pairs in ((raw, 1_000_000), (shifted, 30_000_000)):
+        idx, sl = ops.ballquery(pts, bidx, offs, cfg.cluster_radius)
+        o_idx, o_sl = oracle.ballquery(pts.cpu().numpy(), bidx.cpu().numpy(), offs.cpu().numpy(), cfg.cluster_radius)
+        assert o_idx.size > min_pairs
+        assert np.array_equal(sl.cpu().numpy(), o_sl)
+        assert np.array_equal(idx.cpu().numpy(), o_idx)
+        ci, co = pointgroup_ops.pg_bfs_cluster(lab, idx, sl, cfg.cluster_npoint_thre)
+        w_ci, w_co = oracle.pg_bfs_cluster(lab.cpu().numpy(), o_idx, o_sl, cfg.cluster_npoint_thre)
+        assert w_co.size > 10
+        assert np.array_equal(co.cpu().numpy(), w_co)
+        assert np.array_equal(ci.cpu().numpy(), w_ci)

@@ -249,3 +249,38 @@ def test_loader_size_hints_remove_host_reads_and_are_validated(batch):
     with pytest.raises(ValueError, match="claimed"):
         ops.run_deferred_checks()
     ops.run_deferred_checks()  # the list is empty again
+
+
+def test_fused_bn_relu_updown_conv_equals_module_by_module(batch, monkeypatch):
+    """b2s_bnconv_forward/backward (BN -> ReLU -> strided / transposed convolution of a U-Net level as one call,
+    common.py:67-77) against the module-by-module path on a two-level U-Net: identical features, input gradient,
+    BatchNorm gradients and running statistics (same kernels, same order); weight gradients to 1e-5."""
+    from minsu3d_b200 import MinkowskiEngine as ME
+    from minsu3d_b200.harness import models
+    coords = batch["voxel_xyz"][:20000].contiguous()
+    torch.manual_seed(0)
+    net = models.TinyUnet(16).cuda().train()
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+    x0 = torch.randn(coords.size(0), 16, device="cuda")
+    g = None
+    res = []
+    for fused in (False, True):
+        monkeypatch.setattr(models, "FUSED_UPDOWN", fused)
+        net.load_state_dict(state)
+        net.zero_grad(set_to_none=True)
+        xa = x0.clone().requires_grad_(True)
+        y = net(ME.SparseTensor(features=xa, coordinates=coords)).F
+        g = torch.randn_like(y) if g is None else g
+        y.backward(g)
+        res.append((y.detach().clone(), xa.grad.clone(), {k: p.grad.clone() for k, p in net.named_parameters()},
+                    {k: v.clone() for k, v in net.state_dict().items()}))
+    (ya, gxa, ga, sa), (yb, gxb, gb, sb) = res
+    assert torch.equal(ya, yb) and torch.equal(gxa, gxb)
+    for k in ga:
+        if k.endswith("kernel"):
+            assert _rel(gb[k].cpu().numpy(), ga[k].cpu().numpy()) < 1e-5, k
+        else:
+            assert torch.equal(ga[k], gb[k]), k
+    for k in sa:
+        if not k.endswith("kernel"):
+            assert torch.equal(sa[k], sb[k]), k
