@@ -114,19 +114,30 @@ int b2s_pairs_from_nbr(const int32_t* nbr, int64_t n_out, int32_t K, int64_t pai
  * algo: 0 = auto (tcgen05 3xTF32 when c_in, c_out are multiples of 16 and c_out <= 256, else fp32 FMA),
  *       1 = fp32 FMA (SIMT), 2 = tcgen05 3xTF32 (fp32-class accuracy), 3 = tcgen05 plain TF32.
  * ---------------------------------------------------------------------------------------------- */
-size_t b2s_conv_ws_bytes(int32_t K, int32_t c_in, int32_t c_out); /* scratch for the packed weights */
-int b2s_conv_table(const float* A, const float* W, const int32_t* nbr, const uint32_t* tile_mask,
+size_t b2s_conv_ws_bytes(int32_t K, int32_t c_in, int32_t c_out); /* scratch: packed weights + split partial sums */
+/* Packed weights.  The tcgen05 kernels read W as SWIZZLE_64B shared-memory images split into TF32 hi / lo parts.
+ * b2s_conv_pack writes BOTH orientations of W[K][c_in][c_out] -- [forward hi | forward lo | transposed hi |
+ * transposed lo], b2s_conv_packed_floats() floats (0 = shape not taken by the tcgen05 path) -- in one launch; a caller
+ * that keeps the result while W is unchanged (once per optimizer step) passes it as `Wp` to the products below and
+ * no packing happens there.  Wp == NULL: the product packs the one image it needs into its workspace (round-1
+ * behaviour: 170 extra launches per PointGroup step).                                                          */
+int64_t b2s_conv_packed_floats(int32_t K, int32_t c_in, int32_t c_out);
+int b2s_conv_pack(const float* W, float* Wp, int32_t K, int32_t c_in, int32_t c_out, b2s_stream_t stream);
+/* add_src (optional, [n_out, c_out]): residual added to the result (common.py:48), folded into the epilogue of the
+ * tcgen05 kernel.                                                                                              */
+int b2s_conv_table(const float* A, const float* W, const float* Wp, const int32_t* nbr, const uint32_t* tile_mask,
+                   const float* add_src,
                    float* out, int64_t n_out, int32_t K, int32_t c_in, int32_t c_out,
                    int32_t w_transposed, int32_t k_reversed, int32_t algo,
                    void* ws, size_t ws_bytes, b2s_stream_t stream);
 /* b2s_conv_table over mask-sorted tiles (b2s_tile_order below): row t of the permuted table is stored at
  * out[out_rows[t], :]; same sum, same k order, fewer all-empty (tile, offset) slabs.  tcgen05 path only
  * (c_in, c_out multiples of 16, K <= 32; algo 0/2 = 3xTF32, 3 = TF32; algo 1 is rejected).            */
-int b2s_conv_table_rows(const float* A, const float* W, const int32_t* nbr_sorted, const uint32_t* tile_mask,
-                        const int32_t* out_rows, float* out, int64_t n_out, int32_t K, int32_t c_in,
-                        int32_t c_out, int32_t w_transposed, int32_t k_reversed, int32_t algo,
-                        void* ws, size_t ws_bytes, b2s_stream_t stream);
-int b2s_conv_pairs(const float* A, const float* W, const int32_t* src, const int32_t* dst,
+int b2s_conv_table_rows(const float* A, const float* W, const float* Wp, const int32_t* nbr_sorted,
+                        const uint32_t* tile_mask, const int32_t* out_rows, const float* add_src, float* out,
+                        int64_t n_out, int32_t K, int32_t c_in, int32_t c_out, int32_t w_transposed,
+                        int32_t k_reversed, int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream);
+int b2s_conv_pairs(const float* A, const float* W, const float* Wp, const int32_t* src, const int32_t* dst,
                    const int32_t* k_offsets, float* out, int32_t K, int32_t c_in, int32_t c_out,
                    int32_t w_transposed, int64_t max_pairs, int32_t algo,
                    void* ws, size_t ws_bytes, b2s_stream_t stream);
@@ -160,6 +171,11 @@ int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, 
                     const float* mean, const float* rstd, const float* gamma, int32_t relu,
                     int32_t training, float* dx, float* dgamma, float* dbeta, int32_t* counter,
                     void* ws, size_t ws_bytes, b2s_stream_t stream);
+/* the same with dx += add_src ([n,C]; the gradient arriving over a residual shortcut) in the dx pass */
+int b2s_bn_backward_add(const float* x, const float* y, const float* dy, const float* add_src, int64_t n, int32_t c,
+                        const float* mean, const float* rstd, const float* gamma, int32_t relu,
+                        int32_t training, float* dx, float* dgamma, float* dbeta, int32_t* counter,
+                        void* ws, size_t ws_bytes, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * T3 + T5 host-side fusion -- one MinkUNet residual block per call (minsu3d/model/module/common.py:21-50):
@@ -173,20 +189,25 @@ int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, 
  *   stats1 [2,c_in] / stats2 [2,c_out] = (mean, rstd); tmp [n,c_out] is scratch for the 1x1 shortcut (Wds != NULL).
  *   backward: pair lists of the same map (b2s_pairs_from_nbr) for the weight gradients; ident [n] = 0..n-1 and
  *   ident_koff = {0, n} drive the 1x1 weight gradient; dgb1 [2,c_in] / dgb2 [2,c_out] = (dgamma, dbeta);
- *   tmp_a, tmp_b [n,c_out] and tmp_c [n,c_in] are scratch.
+ *   tmp_a [n,max(c_in,c_out)], tmp_b [n,c_out] and tmp_c [n,c_in] are scratch.
+ *   Wp1 / Wp2 / Wpds (each may be NULL): b2s_conv_pack images of W1 / W2 / Wds.
+ *   The shortcut is added in the epilogue of the second convolution (forward) and in the dx pass of the first
+ *   BatchNorm's backward: no separate add kernels.
  * ---------------------------------------------------------------------------------------------- */
 size_t b2s_resblock_ws_bytes(int32_t K, int32_t c_in, int32_t c_out);
 int b2s_resblock_forward(const float* x, int64_t n, int32_t c_in, int32_t c_out,
                          const float* gamma1, const float* beta1, float* rmean1, float* rvar1, const float* W1,
                          const float* gamma2, const float* beta2, float* rmean2, float* rvar2, const float* W2,
-                         const float* Wds, float eps1, float mom1, float eps2, float mom2,
+                         const float* Wds, const float* Wp1, const float* Wp2, const float* Wpds,
+                         float eps1, float mom1, float eps2, float mom2,
                          const int32_t* nbr, const uint32_t* tile_mask, const int32_t* nbr_sorted,
                          const uint32_t* tile_mask_sorted, const int32_t* row_perm, int32_t K,
                          float* y1, float* stats1, float* z1, float* y2, float* stats2, float* out, float* tmp,
                          int32_t* bn_counter, int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_resblock_backward(const float* gout, const float* x, const float* y1, const float* z1, const float* y2,
                           const float* stats1, const float* stats2, const float* gamma1, const float* gamma2,
-                          const float* W1, const float* W2, const float* Wds, int64_t n, int32_t c_in, int32_t c_out,
+                          const float* W1, const float* W2, const float* Wds, const float* Wp1, const float* Wp2,
+                          const float* Wpds, int64_t n, int32_t c_in, int32_t c_out,
                           const int32_t* nbr, const uint32_t* tile_mask, const int32_t* nbr_sorted,
                           const uint32_t* tile_mask_sorted, const int32_t* row_perm, int32_t K,
                           const int32_t* pair_in, const int32_t* pair_out, const int32_t* k_offsets, int64_t max_pairs,
@@ -199,15 +220,16 @@ int b2s_resblock_backward(const float* gout, const float* x, const float* y1, co
  * of a U-Net level as one call; the strided map fine -> coarse is passed as its table nbr[n_coarse, K] and its
  * pair lists (pair_in = fine row, pair_out = coarse row).  x has n_fine rows in mode 0 and n_coarse rows in mode 1.
  * Saves y = relu(bn(x)) and stats [2,c_in] = (mean, rstd); backward needs tmp [n_x, c_in] scratch, dgb [2,c_in].
- * Experimental in round 1: not yet exercised on a GPU, the harness keeps it switched off.                       */
+ * Wp (may be NULL): b2s_conv_pack image of W.                                                                    */
 int b2s_bnconv_forward(const float* x, int64_t n_x, int32_t c_in, int32_t c_out, const float* gamma, const float* beta,
-                       float* rmean, float* rvar, float eps, float mom, const float* W, int32_t mode,
+                       float* rmean, float* rvar, float eps, float mom, const float* W, const float* Wp, int32_t mode,
                        const int32_t* nbr, const uint32_t* tile_mask, const int32_t* pair_in, const int32_t* pair_out,
                        const int32_t* k_offsets, int64_t max_pairs, int64_t n_coarse, int64_t n_fine, int32_t K,
                        float* y, float* stats, float* out, int32_t* bn_counter, int32_t algo, void* ws, size_t ws_bytes,
                        b2s_stream_t stream);
 int b2s_bnconv_backward(const float* gout, const float* x, const float* y, const float* stats, const float* gamma,
-                        const float* W, int64_t n_x, int32_t c_in, int32_t c_out, int32_t mode, const int32_t* nbr,
+                        const float* W, const float* Wp, int64_t n_x, int32_t c_in, int32_t c_out, int32_t mode,
+                        const int32_t* nbr,
                         const uint32_t* tile_mask, const int32_t* pair_in, const int32_t* pair_out,
                         const int32_t* k_offsets, int64_t max_pairs, int64_t n_coarse, int64_t n_fine, int32_t K,
                         float* gx, float* gW, float* dgb, float* tmp, int32_t* bn_counter, int32_t algo, void* ws,

@@ -22,13 +22,15 @@ class _ConvSame(torch.autograd.Function):
     """Stride-1 odd-size convolution on one coordinate map: symmetric kernel map."""
 
     @staticmethod
-    def forward(ctx, feats, kernel, kmap):
+    def forward(ctx, feats, kernel, kmap, packed=None):
         feats = feats.contiguous()
         K, cin, cout = kernel.shape
         nbr, tile_mask, out_rows = kmap.table_for(cin, cout)
-        out = ops.conv_table(feats, kernel, nbr, kmap.n_out, K, cin, cout, tile_mask=tile_mask, out_rows=out_rows)
+        out = ops.conv_table(feats, kernel, nbr, kmap.n_out, K, cin, cout, tile_mask=tile_mask, out_rows=out_rows,
+                             packed=packed)
         ctx.save_for_backward(feats, kernel)
         ctx.kmap = kmap
+        ctx.packed = packed
         return out
 
     @staticmethod
@@ -42,23 +44,24 @@ class _ConvSame(torch.autograd.Function):
             # nbr[i, K-1-k] = o  <=>  nbr[o, k] = i: reuse the table with reversed, transposed weights
             nbr, tile_mask, out_rows = kmap.table_for(cout, cin)
             gin = ops.conv_table(gout, kernel, nbr, kmap.n_in, K, cout, cin, w_transposed=True, k_reversed=True,
-                                 tile_mask=tile_mask, out_rows=out_rows)
+                                 tile_mask=tile_mask, out_rows=out_rows, packed=ctx.packed)
         if ctx.needs_input_grad[1]:
             pin, pout, koff, maxp = kmap.pairs()
             gk = ops.conv_wgrad(feats, gout, pin, pout, koff, K, cin, cout, maxp)
-        return gin, gk, None
+        return gin, gk, None, None
 
 
 class _ConvDown(torch.autograd.Function):
     """kernel_size == stride (2) convolution: fine -> coarse, table nbr[coarse, 8] of fine rows."""
 
     @staticmethod
-    def forward(ctx, feats, kernel, kmap):
+    def forward(ctx, feats, kernel, kmap, packed=None):
         feats = feats.contiguous()
         K, cin, cout = kernel.shape
-        out = ops.conv_table(feats, kernel, kmap.nbr, kmap.n_out, K, cin, cout, tile_mask=kmap.tile_mask)
+        out = ops.conv_table(feats, kernel, kmap.nbr, kmap.n_out, K, cin, cout, tile_mask=kmap.tile_mask, packed=packed)
         ctx.save_for_backward(feats, kernel)
         ctx.kmap = kmap
+        ctx.packed = packed
         return out
 
     @staticmethod
@@ -71,10 +74,11 @@ class _ConvDown(torch.autograd.Function):
         gin = gk = None
         if ctx.needs_input_grad[0]:
             # every fine row has exactly one (coarse row, offset): plain store, no accumulation
-            gin = ops.conv_pairs(gout, kernel, pout, pin, koff, kmap.n_in, K, cout, cin, maxp, w_transposed=True)
+            gin = ops.conv_pairs(gout, kernel, pout, pin, koff, kmap.n_in, K, cout, cin, maxp, w_transposed=True,
+                                 packed=ctx.packed)
         if ctx.needs_input_grad[1]:
             gk = ops.conv_wgrad(feats, gout, pin, pout, koff, K, cin, cout, maxp)
-        return gin, gk, None
+        return gin, gk, None, None
 
 
 class _ConvUp(torch.autograd.Function):
@@ -84,13 +88,14 @@ class _ConvUp(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, feats, kernel, kmap):
+    def forward(ctx, feats, kernel, kmap, packed=None):
         feats = feats.contiguous()
         K, cin, cout = kernel.shape
         pin, pout, koff, maxp = kmap.pairs()
-        out = ops.conv_pairs(feats, kernel, pout, pin, koff, kmap.n_in, K, cin, cout, maxp)
+        out = ops.conv_pairs(feats, kernel, pout, pin, koff, kmap.n_in, K, cin, cout, maxp, packed=packed)
         ctx.save_for_backward(feats, kernel)
         ctx.kmap = kmap
+        ctx.packed = packed
         return out
 
     @staticmethod
@@ -102,11 +107,11 @@ class _ConvUp(torch.autograd.Function):
         gin = gk = None
         if ctx.needs_input_grad[0]:
             gin = ops.conv_table(gout, kernel, kmap.nbr, kmap.n_out, K, cout, cin, w_transposed=True,
-                                 tile_mask=kmap.tile_mask)
+                                 tile_mask=kmap.tile_mask, packed=ctx.packed)
         if ctx.needs_input_grad[1]:
             pin, pout, koff, maxp = kmap.pairs()
             gk = ops.conv_wgrad(feats, gout, pout, pin, koff, K, cin, cout, maxp)
-        return gin, gk, None
+        return gin, gk, None, None
 
 
 _IDENT = {}
@@ -128,11 +133,12 @@ class _Conv1x1(torch.autograd.Function):
     """kernel_size 1, stride 1: dense [M,Cin] @ [Cin,Cout] through the same implicit-GEMM kernel."""
 
     @staticmethod
-    def forward(ctx, feats, kernel):
+    def forward(ctx, feats, kernel, packed=None):
         feats = feats.contiguous()
         cin, cout = kernel.shape
-        out = ops.conv_table(feats, kernel, None, feats.size(0), 1, cin, cout)
+        out = ops.conv_table(feats, kernel, None, feats.size(0), 1, cin, cout, packed=packed)
         ctx.save_for_backward(feats, kernel)
+        ctx.packed = packed
         return out
 
     @staticmethod
@@ -142,12 +148,12 @@ class _Conv1x1(torch.autograd.Function):
         gout = gout.contiguous()
         gin = gk = None
         if ctx.needs_input_grad[0]:
-            gin = ops.conv_table(gout, kernel, None, feats.size(0), 1, cout, cin, w_transposed=True)
+            gin = ops.conv_table(gout, kernel, None, feats.size(0), 1, cout, cin, w_transposed=True, packed=ctx.packed)
         if ctx.needs_input_grad[1]:
             n = feats.size(0)
             ident, koff = _identity_pairs(n, feats.device)
             gk = ops.conv_wgrad(feats, gout, ident, ident, koff, 1, cin, cout, n).view(cin, cout)
-        return gin, gk
+        return gin, gk, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -186,7 +192,14 @@ class _ConvBase(nn.Module):
             shape = (self.kernel_volume, in_channels, out_channels)
         self.kernel = nn.Parameter(torch.empty(shape, dtype=torch.float32))
         self.bias = nn.Parameter(torch.empty(1, out_channels, dtype=torch.float32)) if bias else None
+        self._packed = ops.PackedWeights()  # tensor-core operand images of `kernel`, re-packed when it changes
         self.reset_parameters(is_transpose)
+
+    def packed(self):
+        """conv_pack(kernel), cached until the parameter is modified (None: shape not on the tcgen05 path / CPU)."""
+        if ops.get_conv_algo() == ops.ALGO_SIMT:
+            return None
+        return self._packed.get(self.kernel)
 
     def reset_parameters(self, is_transpose=False):
         with torch.no_grad():
@@ -215,17 +228,17 @@ class MinkowskiConvolution(_ConvBase):
     def forward(self, x):
         mgr, key = x.coordinate_manager, x.coordinate_map_key
         if self.use_mm:
-            return self._finish(x, _Conv1x1.apply(x.F, self.kernel), key)
+            return self._finish(x, _Conv1x1.apply(x.F, self.kernel, self.packed()), key)
         if self.stride == 1:
             if self.kernel_size % 2 != 1:
                 raise NotImplementedError("stride-1 convolutions need an odd kernel size")
             kmap = mgr.kernel_map(key, key, self.kernel_size)
-            return self._finish(x, _ConvSame.apply(x.F, self.kernel, kmap), key)
+            return self._finish(x, _ConvSame.apply(x.F, self.kernel, kmap, self.packed()), key)
         if self.stride != self.kernel_size:
             raise NotImplementedError("strided convolution is supported for kernel_size == stride (2/2)")
         out_key = mgr.stride_key(key, self.stride)
         kmap = mgr.kernel_map(key, out_key, self.kernel_size)
-        return self._finish(x, _ConvDown.apply(x.F, self.kernel, kmap), out_key)
+        return self._finish(x, _ConvDown.apply(x.F, self.kernel, kmap, self.packed()), out_key)
 
 
 class MinkowskiConvolutionTranspose(_ConvBase):
@@ -237,12 +250,12 @@ class MinkowskiConvolutionTranspose(_ConvBase):
     def forward(self, x):
         mgr, key = x.coordinate_manager, x.coordinate_map_key
         if self.use_mm:
-            return self._finish(x, _Conv1x1.apply(x.F, self.kernel), key)
+            return self._finish(x, _Conv1x1.apply(x.F, self.kernel, self.packed()), key)
         if self.stride != self.kernel_size or key.stride % self.stride != 0:
             raise NotImplementedError("transposed convolution is supported for kernel_size == stride (2/2)")
         fine_key = mgr.existing_key(key.stride // self.stride)  # the encoder's map (appendix A.6)
         kmap = mgr.kernel_map(fine_key, key, self.kernel_size)
-        return self._finish(x, _ConvUp.apply(x.F, self.kernel, kmap), fine_key)
+        return self._finish(x, _ConvUp.apply(x.F, self.kernel, kmap, self.packed()), fine_key)
 
 
 # ---- normalisation / activation -------------------------------------------------------------
@@ -414,7 +427,7 @@ class _ResBlockFn(torch.autograd.Function):
     module-by-module path (same kernels in the same order), but 1 node / 1 call instead of 5-6 each."""
 
     @staticmethod
-    def forward(ctx, x, g1, b1, w1, g2, b2, w2, wds, bn1, bn2, kmap):
+    def forward(ctx, x, g1, b1, w1, g2, b2, w2, wds, bn1, bn2, kmap, wp1=None, wp2=None, wpds=None):
         x = x.contiguous()
         n, cin = x.shape
         cout = w1.size(2)
@@ -436,7 +449,8 @@ class _ResBlockFn(torch.autograd.Function):
             x.data_ptr(), n, cin, cout,
             g1.data_ptr(), b1.data_ptr(), ops.ptr(bn1.running_mean), ops.ptr(bn1.running_var), w1.data_ptr(),
             g2.data_ptr(), b2.data_ptr(), ops.ptr(bn2.running_mean), ops.ptr(bn2.running_var), w2.data_ptr(),
-            ops.ptr(wds), bn1.eps, bn1.momentum if bn1.running_mean is not None else 0.0,
+            ops.ptr(wds), ops.ptr(wp1), ops.ptr(wp2), ops.ptr(wpds),
+            bn1.eps, bn1.momentum if bn1.running_mean is not None else 0.0,
             bn2.eps, bn2.momentum if bn2.running_mean is not None else 0.0,
             kmap.nbr.data_ptr(), ops.ptr(kmap.tile_mask), ops.ptr(nbr_s), ops.ptr(mask_s), ops.ptr(perm), K,
             p_y1, p_s1, p_z1, p_y2, p_s2, out.data_ptr(), ops.ptr(tmp),
@@ -444,6 +458,7 @@ class _ResBlockFn(torch.autograd.Function):
         ctx.save_for_backward(x, saved, g1, g2, w1, w2, wds)
         ctx.kmap = kmap
         ctx.algo = algo
+        ctx.packed = (wp1, wp2, wpds)
         return out
 
     @staticmethod
@@ -465,9 +480,10 @@ class _ResBlockFn(torch.autograd.Function):
         gwds = torch.empty_like(wds) if wds is not None else None
         dgb1 = torch.empty((2, cin), dtype=torch.float32, device=dev)
         dgb2 = torch.empty((2, cout), dtype=torch.float32, device=dev)
-        scratch = torch.empty(n * (2 * cout + cin), dtype=torch.float32, device=dev)
-        p_a = scratch.data_ptr()
-        p_b = p_a + 4 * n * cout
+        wp1, wp2, wpds = ctx.packed
+        scratch = torch.empty(n * (max(cin, cout) + cout + cin), dtype=torch.float32, device=dev)
+        p_a = scratch.data_ptr()  # [n, max(cin, cout)]: conv2 data gradient, later the 1x1 shortcut's data gradient
+        p_b = p_a + 4 * n * max(cin, cout)
         p_c = p_b + 4 * n * cout
         pin, pout, koff, maxp = kmap.pairs()
         ident = ident_koff = None
@@ -477,13 +493,13 @@ class _ResBlockFn(torch.autograd.Function):
         ws = ops.workspace(ops.resblock_ws_bytes(K, cin, cout), dev)
         ops.check(ops.lib().b2s_resblock_backward(
             gout.data_ptr(), x.data_ptr(), p_y1, p_z1, p_y2, p_s1, p_s2, g1.data_ptr(), g2.data_ptr(),
-            w1.data_ptr(), w2.data_ptr(), ops.ptr(wds), n, cin, cout,
+            w1.data_ptr(), w2.data_ptr(), ops.ptr(wds), ops.ptr(wp1), ops.ptr(wp2), ops.ptr(wpds), n, cin, cout,
             kmap.nbr.data_ptr(), ops.ptr(kmap.tile_mask), ops.ptr(nbr_s), ops.ptr(mask_s), ops.ptr(perm), K,
             pin.data_ptr(), pout.data_ptr(), koff.data_ptr(), int(maxp), ops.ptr(ident), ops.ptr(ident_koff),
             gx.data_ptr(), gw1.data_ptr(), gw2.data_ptr(), ops.ptr(gwds), dgb1.data_ptr(), dgb2.data_ptr(),
             p_a, p_b, p_c, ops.bn_counter(dev).data_ptr(), ctx.algo, ws.data_ptr(), ws.numel(), ops.stream()),
             "resblock_backward")
-        return gx, dgb1[0], dgb1[1], gw1, dgb2[0], dgb2[1], gw2, gwds, None, None, None
+        return gx, dgb1[0], dgb1[1], gw1, dgb2[0], dgb2[1], gw2, gwds, None, None, None, None, None, None
 
 
 def residual_block_fusable(x, bn1, conv1, bn2, conv2, downsample):
@@ -506,16 +522,17 @@ def fused_residual_block(x, bn1, conv1, bn2, conv2, downsample=None):
     b1, b2 = bn1.bn, bn2.bn
     torch._foreach_add_([b1.num_batches_tracked, b2.num_batches_tracked], 1)
     out = _ResBlockFn.apply(x.F, b1.weight, b1.bias, conv1.kernel, b2.weight, b2.bias, conv2.kernel,
-                            None if downsample is None else downsample.kernel, b1, b2, kmap)
+                            None if downsample is None else downsample.kernel, b1, b2, kmap,
+                            conv1.packed(), conv2.packed(), None if downsample is None else downsample.packed())
     return SparseTensor(out, coordinate_map_key=key, coordinate_manager=mgr)
 
 
 class _BnReluConvFn(torch.autograd.Function):
     """relu(bn(x)) -> strided convolution (mode 0) / transposed convolution (mode 1) of a U-Net level in one call
-    (csrc/fused.cu: b2s_bnconv_forward/backward).  EXPERIMENTAL: not yet exercised on a GPU."""
+    (csrc/fused.cu: b2s_bnconv_forward/backward)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, kernel, bn, kmap, mode):
+    def forward(ctx, x, gamma, beta, kernel, bn, kmap, mode, packed=None):
         x = x.contiguous()
         n_x, cin = x.shape
         K, _, cout = kernel.shape
@@ -532,11 +549,11 @@ class _BnReluConvFn(torch.autograd.Function):
         ops.check(ops.lib().b2s_bnconv_forward(
             x.data_ptr(), n_x, cin, cout, gamma.data_ptr(), beta.data_ptr(), ops.ptr(bn.running_mean),
             ops.ptr(bn.running_var), bn.eps, bn.momentum if bn.running_mean is not None else 0.0, kernel.data_ptr(),
-            int(mode), kmap.nbr.data_ptr(), ops.ptr(kmap.tile_mask), pin.data_ptr(), pout.data_ptr(), koff.data_ptr(),
+            ops.ptr(packed), int(mode), kmap.nbr.data_ptr(), ops.ptr(kmap.tile_mask), pin.data_ptr(), pout.data_ptr(), koff.data_ptr(),
             int(maxp), kmap.n_out, kmap.n_in, K, p_y, p_s, out.data_ptr(), ops.bn_counter(dev).data_ptr(), algo,
             ws.data_ptr(), ws.numel(), ops.stream()), "bnconv_forward")
         ctx.save_for_backward(x, saved, gamma, kernel)
-        ctx.kmap, ctx.mode, ctx.algo = kmap, int(mode), algo
+        ctx.kmap, ctx.mode, ctx.algo, ctx.packed = kmap, int(mode), algo, packed
         return out
 
     @staticmethod
@@ -557,11 +574,12 @@ class _BnReluConvFn(torch.autograd.Function):
         c = max(cin, cout)
         ws = ops.workspace(ops.resblock_ws_bytes(K, c, c), dev)
         ops.check(ops.lib().b2s_bnconv_backward(
-            gout.data_ptr(), x.data_ptr(), p_y, p_s, gamma.data_ptr(), kernel.data_ptr(), n_x, cin, cout, mode,
+            gout.data_ptr(), x.data_ptr(), p_y, p_s, gamma.data_ptr(), kernel.data_ptr(), ops.ptr(ctx.packed), n_x, cin,
+            cout, mode,
             kmap.nbr.data_ptr(), ops.ptr(kmap.tile_mask), pin.data_ptr(), pout.data_ptr(), koff.data_ptr(), int(maxp),
             kmap.n_out, kmap.n_in, K, gx.data_ptr(), gw.data_ptr(), dgb.data_ptr(), tmp.data_ptr(),
             ops.bn_counter(dev).data_ptr(), ctx.algo, ws.data_ptr(), ws.numel(), ops.stream()), "bnconv_backward")
-        return gx, dgb[0], dgb[1], gw, None, None, None
+        return gx, dgb[0], dgb[1], gw, None, None, None, None
 
 
 def bn_relu_conv_fusable(x, bn_mod, conv):
@@ -584,5 +602,5 @@ def fused_bn_relu_conv(x, bn_mod, conv):
         kmap = mgr.kernel_map(key, out_key, conv.kernel_size)
         mode = 0
     b.num_batches_tracked += 1
-    out = _BnReluConvFn.apply(x.F, b.weight, b.bias, conv.kernel, b, kmap, mode)
+    out = _BnReluConvFn.apply(x.F, b.weight, b.bias, conv.kernel, b, kmap, mode, conv.packed())
     return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=mgr)

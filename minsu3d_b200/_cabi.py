@@ -31,27 +31,32 @@ _SIGNATURES = {
     "b2s_pairs_ws_bytes": (c_size, [c_i64, c_i32]),
     "b2s_pairs_from_nbr": (c_i32, [_P, c_i64, c_i32, c_i64, _P, _P, _P, _P, _P, c_size, _P]),
     "b2s_conv_ws_bytes": (c_size, [c_i32, c_i32, c_i32]),
-    "b2s_conv_table": (c_i32, [_P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P, c_size, _P]),
-    "b2s_conv_table_rows": (c_i32, [_P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P, c_size,
-                                    _P]),
+    "b2s_conv_packed_floats": (c_i64, [c_i32, c_i32, c_i32]),
+    "b2s_conv_pack": (c_i32, [_P, _P, c_i32, c_i32, c_i32, _P]),
+    "b2s_conv_table": (c_i32, [_P, _P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P, c_size,
+                               _P]),
+    "b2s_conv_table_rows": (c_i32, [_P, _P, _P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P,
+                                    c_size, _P]),
     "b2s_tile_order_ws_bytes": (c_size, [c_i64]),
     "b2s_tile_order": (c_i32, [_P, c_i64, c_i32, _P, _P, _P, _P, c_size, _P]),
-    "b2s_conv_pairs": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, _P, c_size, _P]),
+    "b2s_conv_pairs": (c_i32, [_P, _P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i64, c_i32, _P, c_size, _P]),
     "b2s_conv_wgrad": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i64, c_i32, _P]),
     "b2s_bn_ws_bytes": (c_size, [c_i64, c_i32]),
     "b2s_bn_stats": (c_i32, [_P, c_i64, c_i32, c_f32, c_f32, _P, _P, _P, _P, _P, _P, _P, c_size, _P]),
     "b2s_bn_forward": (c_i32, [_P, c_i64, c_i32, c_f32, c_f32, _P, _P, _P, _P, c_i32, _P, _P, _P, _P, _P, c_size, _P]),
     "b2s_bn_apply": (c_i32, [_P, c_i64, c_i32, _P, _P, _P, _P, c_i32, _P, _P]),
     "b2s_bn_backward": (c_i32, [_P, _P, _P, c_i64, c_i32, _P, _P, _P, c_i32, c_i32, _P, _P, _P, _P, _P, c_size, _P]),
+    "b2s_bn_backward_add": (c_i32, [_P, _P, _P, _P, c_i64, c_i32, _P, _P, _P, c_i32, c_i32, _P, _P, _P, _P, _P, c_size,
+                                    _P]),
     "b2s_resblock_ws_bytes": (c_size, [c_i32, c_i32, c_i32]),
-    "b2s_resblock_forward": (c_i32, [_P, c_i64, c_i32, c_i32] + [_P] * 11 + [c_f32] * 4 + [_P] * 5 + [c_i32] + [_P] * 8 +
+    "b2s_resblock_forward": (c_i32, [_P, c_i64, c_i32, c_i32] + [_P] * 14 + [c_f32] * 4 + [_P] * 5 + [c_i32] + [_P] * 8 +
                              [c_i32, _P, c_size, _P]),
-    "b2s_resblock_backward": (c_i32, [_P] * 12 + [c_i64, c_i32, c_i32] + [_P] * 5 + [c_i32] + [_P] * 3 + [c_i64] +
+    "b2s_resblock_backward": (c_i32, [_P] * 15 + [c_i64, c_i32, c_i32] + [_P] * 5 + [c_i32] + [_P] * 3 + [c_i64] +
                               [_P] * 12 + [c_i32, _P, c_size, _P]),
-    "b2s_bnconv_forward": (c_i32, [_P, c_i64, c_i32, c_i32, _P, _P, _P, _P, c_f32, c_f32, _P, c_i32, _P, _P, _P, _P, _P,
-                                   c_i64, c_i64, c_i64, c_i32, _P, _P, _P, _P, c_i32, _P, c_size, _P]),
-    "b2s_bnconv_backward": (c_i32, [_P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, c_i64, c_i64,
-                                    c_i64, c_i32, _P, _P, _P, _P, _P, c_i32, _P, c_size, _P]),
+    "b2s_bnconv_forward": (c_i32, [_P, c_i64, c_i32, c_i32, _P, _P, _P, _P, c_f32, c_f32, _P, _P, c_i32, _P, _P, _P, _P,
+                                   _P, c_i64, c_i64, c_i64, c_i32, _P, _P, _P, _P, c_i32, _P, c_size, _P]),
+    "b2s_bnconv_backward": (c_i32, [_P, _P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, _P, _P, _P, _P, _P, c_i64,
+                                    c_i64, c_i64, c_i32, _P, _P, _P, _P, _P, c_i32, _P, c_size, _P]),
     "b2s_gather_rows": (c_i32, [_P, _P, c_i64, c_i32, _P, _P]),
     "b2s_scatter_add_rows": (c_i32, [_P, _P, c_i64, c_i32, _P, _P]),
     "b2s_ballquery_ws_bytes": (c_size, [c_i64]),
@@ -112,8 +117,8 @@ class _Namespace:
 # kernels launched by one call of each entry point (CUB scan = 2, 64-bit radix sort ~ 10);
 # used for the `gpu_launches` figure of bench.py
 KERNELS_PER_CALL = {
-    "b2s_coord_unique": 6, "b2s_kernel_map": 1, "b2s_pairs_from_nbr": 4, "b2s_conv_table": 2, "b2s_conv_table_rows": 2, "b2s_tile_order": 7, "b2s_conv_pairs": 2,
-    "b2s_conv_wgrad": 1, "b2s_resblock_forward": 9, "b2s_resblock_backward": 11, "b2s_bnconv_forward": 4, "b2s_bnconv_backward": 5, "b2s_bn_stats": 1, "b2s_bn_forward": 2, "b2s_bn_apply": 1, "b2s_bn_backward": 2, "b2s_gather_rows": 1,
+    "b2s_coord_unique": 6, "b2s_kernel_map": 1, "b2s_pairs_from_nbr": 4, "b2s_conv_pack": 1, "b2s_conv_table": 1, "b2s_conv_table_rows": 1, "b2s_tile_order": 7, "b2s_conv_pairs": 1,
+    "b2s_conv_wgrad": 1, "b2s_resblock_forward": 6, "b2s_resblock_backward": 8, "b2s_bnconv_forward": 3, "b2s_bnconv_backward": 4, "b2s_bn_backward_add": 2, "b2s_bn_stats": 1, "b2s_bn_forward": 2, "b2s_bn_apply": 1, "b2s_bn_backward": 2, "b2s_gather_rows": 1,
     "b2s_scatter_add_rows": 1, "b2s_ballquery_count": 16, "b2s_ballquery_fill": 2, "b2s_cluster_label": 5,
     "b2s_cluster_select": 7, "b2s_cluster_order": 4, "b2s_cluster_centers": 1, "b2s_ha_assign": 1,
     "b2s_ha_concat": 4, "b2s_sec_mean": 1, "b2s_sec_min": 1, "b2s_sec_max": 1, "b2s_roipool_fp": 1,

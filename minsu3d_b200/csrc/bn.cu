@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256)
                  int64_t total4, int c4, float inv_n, const float* __restrict__ mean,
                  const float* __restrict__ rstd, const float* __restrict__ gamma,
                  const float* __restrict__ dgamma, const float* __restrict__ dbeta, int relu,
-                 int training, float4* __restrict__ dx) {
+                 int training, const float4* __restrict__ add_src, float4* __restrict__ dx) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total4) return;
   int ch = (int)(t % c4) * 4;
@@ -235,6 +235,13 @@ __global__ void __launch_bounds__(256)
     } else {
       o[j] = sc * gs[j];
     }
+  }
+  if (add_src != nullptr) {  // gradient arriving over the residual shortcut (common.py:48), folded into this pass
+    const float4 av = __ldg(add_src + t);
+    o[0] += av.x;
+    o[1] += av.y;
+    o[2] += av.z;
+    o[3] += av.w;
   }
   dx[t] = make_float4(o[0], o[1], o[2], o[3]);
 }
@@ -320,6 +327,14 @@ int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, 
                     const float* mean, const float* rstd, const float* gamma, int32_t relu,
                     int32_t training, float* dx, float* dgamma, float* dbeta, int32_t* counter, void* ws,
                     size_t ws_bytes, b2s_stream_t stream) {
+  return b2s_bn_backward_add(x, y, dy, nullptr, n, c, mean, rstd, gamma, relu, training, dx, dgamma, dbeta, counter, ws,
+                             ws_bytes, stream);
+}
+
+int b2s_bn_backward_add(const float* x, const float* y, const float* dy, const float* add_src, int64_t n, int32_t c,
+                        const float* mean, const float* rstd, const float* gamma, int32_t relu,
+                        int32_t training, float* dx, float* dgamma, float* dbeta, int32_t* counter, void* ws,
+                        size_t ws_bytes, b2s_stream_t stream) {
   int rc = bn_check(n, c);
   if (rc) return rc;
   if (n == 0) {
@@ -339,7 +354,7 @@ int b2s_bn_backward(const float* x, const float* y, const float* dy, int64_t n, 
   int64_t total4 = n * (c / 4);
   bn_dx_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, stream>>>(
       (const float4*)x, (const float4*)y, (const float4*)dy, total4, c / 4, 1.0f / (float)n, mean, rstd,
-      gamma, dgamma, dbeta, relu, training, (float4*)dx);
+      gamma, dgamma, dbeta, relu, training, (const float4*)add_src, (float4*)dx);
   return check_launch("bn_backward");
 }
 

@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace b2s {
 
@@ -41,117 +42,6 @@ namespace b2s {
 #define B2S_TC_IDX_AHEAD 0
 #endif
 
-constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 192;  // warps 0-3: gather producers + epilogue, warp 4: MMA issuer, warp 5: weight loader
-constexpr int TC_A_SLAB = TC_BM * 64;  // bytes
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-// one lane of a converged warp (ELECT): keeps the surrounding control flow warp-uniform, so descriptors and
-// barrier addresses stay in uniform registers (a lane == 0 branch makes ptxas wrap every tcgen05/UBLKCP
-// instruction in a R2UR waterfall loop: ~40 instructions and ~80 cycles per MMA, measured)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
-      : "memory");
-}
-// TS form: A operand from tensor memory (lane = tile row, 8 consecutive 32-bit columns per K = 8 slice)
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(0u)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major) | SBO>>4 [32,46) = 512 B between
-// 8-row groups | version=1 [46,48) | layout_type=4 (SWIZZLE_64B) [61,64)
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)4 << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
-// a/b K-major, N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
-__host__ __device__ __forceinline__ int sw64_offset(int row, int j) {  // byte offset inside a slab
-  return row * 64 + ((((j >> 2) ^ ((row >> 1) & 3))) << 4) + (j & 3) * 4;
-}
-
 // ---------------------------------------------------------------------------------------------
 // weight packing: W[K][c_in][c_out] (or its transpose view) -> per-slab SW64 images, hi then lo
 // ---------------------------------------------------------------------------------------------
@@ -160,6 +50,17 @@ __global__ void __launch_bounds__(256)
                         int w_transposed, int64_t total) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
+  if (gridDim.y == 2) {
+    // both orientations in one launch (b2s_conv_pack): y = 0 the forward image pair, y = 1 the transposed pair for the
+    // data gradient, which is a c_out -> c_in product: roles of the two channel counts swap
+    Bp += (int64_t)blockIdx.y * 2 * total;
+    if (blockIdx.y == 1) {
+      w_transposed = 1;
+      const int t = c_in;
+      c_in = c_out;
+      c_out = t;
+    }
+  }
   const int per_slab = c_out * 16;
   int64_t slab = e / per_slab;
   int within = (int)(e - slab * per_slab);
@@ -575,8 +476,10 @@ bool conv_tc_supported(int K, int c_in, int c_out) {
   return K >= 1 && K <= 32 && c_in >= 16 && (c_in % 16) == 0 && c_out >= 16 && (c_out % 16) == 0 && c_out <= 256;
 }
 
+size_t conv_tcp_split_ws_bytes();
+
 size_t conv_tc_ws_bytes(int K, int c_in, int c_out) {
-  return align_up((size_t)K * c_in * c_out * 4 * 2) + 256 + (tc_split_enabled() ? TC_SPLIT_WS + 256 : 0);
+  return align_up((size_t)K * c_in * c_out * 4 * 2) + 256 + conv_tcp_split_ws_bytes();
 }
 
 template <bool PAIRS, int NSPLIT>
@@ -613,8 +516,27 @@ static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream, int splits =
   return check_launch("conv_tc");
 }
 
-// ws: packed weights, conv_tc_ws_bytes(K, c_in, c_out) bytes
-int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* dst, const int32_t* k_offsets,
+// W[K][c_in][c_out] -> [fwd hi | fwd lo | transposed hi | transposed lo], 4 * K * c_in * c_out floats, one launch.
+// The transposed pair is the operand of the data gradient (a c_out -> c_in product with w_transposed = 1).
+int conv_tc_pack_both(const float* W, float* Bp, int K, int c_in, int c_out, cudaStream_t stream) {
+  const int64_t half = (int64_t)K * c_in * c_out;
+  if (half == 0) return B2S_OK;
+  pack_weights_kernel<<<dim3((unsigned)cdiv(half, 256), 2), 256, 0, stream>>>(W, Bp, K, c_in, c_out, 0, half);
+  return check_launch("conv_pack");
+}
+
+// the image pair one product needs: packed by the caller (Wp, both orientations) or packed here into ws
+const float* conv_tc_weights(const float* W, const float* Wp, int K, int c_in, int c_out, int wT, void* ws,
+                             cudaStream_t stream) {
+  const int64_t half = (int64_t)K * c_in * c_out;
+  if (Wp != nullptr) return Wp + (wT ? 2 * half : 0);
+  float* Bp = (float*)ws;
+  pack_weights_kernel<<<(unsigned)cdiv(half, 256), 256, 0, stream>>>(W, Bp, K, c_in, c_out, wT, half);
+  return Bp;
+}
+
+// ws: conv_tc_ws_bytes(K, c_in, c_out) bytes (packed weights when Wp == NULL, split scratch)
+int conv_tc(const float* A, const float* W, const float* Wp, const int32_t* idx, const int32_t* dst, const int32_t* k_offsets,
             const uint32_t* tile_mask, const int32_t* out_rows, float* out, int64_t n_out, int64_t max_pairs, int K, int c_in, int c_out, int wT, int krev, int nsplit,
             bool pairs, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (ws_bytes < conv_tc_ws_bytes(K, c_in, c_out)) {
@@ -623,8 +545,7 @@ int conv_tc(const float* A, const float* W, const int32_t* idx, const int32_t* d
   }
   if ((!pairs && n_out == 0) || (pairs && max_pairs == 0)) return B2S_OK;
   int64_t half = (int64_t)K * c_in * c_out;
-  float* Bp = (float*)ws;
-  pack_weights_kernel<<<(unsigned)cdiv(half, 256), 256, 0, stream>>>(W, Bp, K, c_in, c_out, wT, half);
+  const float* Bp = conv_tc_weights(W, Wp, K, c_in, c_out, wT, ws, stream);
   TcArgs a;
   a.A = A;
   a.Bp = Bp;

@@ -12,25 +12,7 @@
 
 namespace b2s {
 
-__global__ void __launch_bounds__(256)
-    add_inplace_kernel(float4* __restrict__ y, const float4* __restrict__ s, int64_t total4) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total4) return;
-  float4 a = y[i];
-  const float4 b = __ldg(s + i);
-  a.x += b.x;
-  a.y += b.y;
-  a.z += b.z;
-  a.w += b.w;
-  y[i] = a;
-}
-
-static int add_inplace(float* y, const float* s, int64_t n, int c, cudaStream_t stream) {
-  const int64_t total4 = n * (c / 4);
-  if (total4 == 0) return B2S_OK;
-  add_inplace_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, stream>>>((float4*)y, (const float4*)s, total4);
-  return check_launch("resblock add");
-}
+int add_rows(float* y, const float* s, int64_t n, int c, cudaStream_t stream);
 
 bool conv_tc_supported(int K, int c_in, int c_out);
 
@@ -44,12 +26,15 @@ struct Tables {
 };
 
 // stride-1 3^3 product on the block's map: sorted tiles when the caller built them and the tcgen05 path applies
-static int conv_same(const float* A, const float* W, float* out, int64_t n, int c_in, int c_out, int wT, int krev,
-                     int algo, const Tables& t, void* ws, size_t ws_bytes, cudaStream_t stream) {
+// add_src (optional): residual folded into the convolution's epilogue (tcgen05 path) or added right after (FMA path)
+static int conv_same(const float* A, const float* W, const float* Wp, const float* add_src, float* out, int64_t n,
+                     int c_in, int c_out, int wT, int krev, int algo, const Tables& t, void* ws, size_t ws_bytes,
+                     cudaStream_t stream) {
   if (t.nbr_sorted != nullptr && algo != 1 && conv_tc_supported(t.K, c_in, c_out))
-    return b2s_conv_table_rows(A, W, t.nbr_sorted, t.tile_mask_sorted, t.row_perm, out, n, t.K, c_in, c_out, wT, krev,
-                               algo, ws, ws_bytes, stream);
-  return b2s_conv_table(A, W, t.nbr, t.tile_mask, out, n, t.K, c_in, c_out, wT, krev, algo, ws, ws_bytes, stream);
+    return b2s_conv_table_rows(A, W, Wp, t.nbr_sorted, t.tile_mask_sorted, t.row_perm, add_src, out, n, t.K, c_in, c_out,
+                               wT, krev, algo, ws, ws_bytes, stream);
+  return b2s_conv_table(A, W, Wp, t.nbr, t.tile_mask, add_src, out, n, t.K, c_in, c_out, wT, krev, algo, ws, ws_bytes,
+                        stream);
 }
 
 }  // namespace b2s
@@ -78,7 +63,8 @@ size_t b2s_resblock_ws_bytes(int32_t K, int32_t c_in, int32_t c_out) {
 int b2s_resblock_forward(const float* x, int64_t n, int32_t c_in, int32_t c_out,
                          const float* gamma1, const float* beta1, float* rmean1, float* rvar1, const float* W1,
                          const float* gamma2, const float* beta2, float* rmean2, float* rvar2, const float* W2,
-                         const float* Wds, float eps1, float mom1, float eps2, float mom2,
+                         const float* Wds, const float* Wp1, const float* Wp2, const float* Wpds,
+                         float eps1, float mom1, float eps2, float mom2,
                          const int32_t* nbr, const uint32_t* tile_mask, const int32_t* nbr_sorted,
                          const uint32_t* tile_mask_sorted, const int32_t* row_perm, int32_t K,
                          float* y1, float* stats1, float* z1, float* y2, float* stats2, float* out, float* tmp,
@@ -101,19 +87,21 @@ int b2s_resblock_forward(const float* x, int64_t n, int32_t c_in, int32_t c_out,
   const Tables t{nbr, tile_mask, nbr_sorted, tile_mask_sorted, row_perm, K};
   // shortcut first (common.py:45), into tmp when it is a 1x1 convolution
   if (Wds != nullptr)
-    B2S_TRY(b2s_conv_table(x, Wds, nullptr, nullptr, tmp, n, 1, c_in, c_out, 0, 0, algo, conv_ws, conv_bytes, stream));
+    B2S_TRY(b2s_conv_table(x, Wds, Wpds, nullptr, nullptr, nullptr, tmp, n, 1, c_in, c_out, 0, 0, algo, conv_ws,
+                           conv_bytes, stream));
   B2S_TRY(b2s_bn_forward(x, n, c_in, eps1, mom1, rmean1, rvar1, gamma1, beta1, 1, y1, stats1, stats1 + c_in, bn_counter,
                          bn_ws, bn_bytes, stream));
-  B2S_TRY(conv_same(y1, W1, z1, n, c_in, c_out, 0, 0, algo, t, conv_ws, conv_bytes, stream));
+  B2S_TRY(conv_same(y1, W1, Wp1, nullptr, z1, n, c_in, c_out, 0, 0, algo, t, conv_ws, conv_bytes, stream));
   B2S_TRY(b2s_bn_forward(z1, n, c_out, eps2, mom2, rmean2, rvar2, gamma2, beta2, 1, y2, stats2, stats2 + c_out,
                          bn_counter, bn_ws, bn_bytes, stream));
-  B2S_TRY(conv_same(y2, W2, out, n, c_out, c_out, 0, 0, algo, t, conv_ws, conv_bytes, stream));
-  return add_inplace(out, Wds != nullptr ? tmp : x, n, c_out, stream);
+  // second convolution with the shortcut added in its epilogue (common.py:48)
+  return conv_same(y2, W2, Wp2, Wds != nullptr ? tmp : x, out, n, c_out, c_out, 0, 0, algo, t, conv_ws, conv_bytes, stream);
 }
 
 int b2s_resblock_backward(const float* gout, const float* x, const float* y1, const float* z1, const float* y2,
                           const float* stats1, const float* stats2, const float* gamma1, const float* gamma2,
-                          const float* W1, const float* W2, const float* Wds, int64_t n, int32_t c_in, int32_t c_out,
+                          const float* W1, const float* W2, const float* Wds, const float* Wp1, const float* Wp2,
+                          const float* Wpds, int64_t n, int32_t c_in, int32_t c_out,
                           const int32_t* nbr, const uint32_t* tile_mask, const int32_t* nbr_sorted,
                           const uint32_t* tile_mask_sorted, const int32_t* row_perm, int32_t K,
                           const int32_t* pair_in, const int32_t* pair_out, const int32_t* k_offsets, int64_t max_pairs,
@@ -137,24 +125,26 @@ int b2s_resblock_backward(const float* gout, const float* x, const float* y1, co
   }
   const Tables t{nbr, tile_mask, nbr_sorted, tile_mask_sorted, row_perm, K};
   // second convolution: data gradient (symmetric map: reversed offsets, transposed weights) and weight gradient
-  B2S_TRY(conv_same(gout, W2, tmp_a, n, c_out, c_out, 1, 1, algo, t, conv_ws, conv_bytes, stream));
+  B2S_TRY(conv_same(gout, W2, Wp2, nullptr, tmp_a, n, c_out, c_out, 1, 1, algo, t, conv_ws, conv_bytes, stream));
   B2S_TRY(b2s_conv_wgrad(y2, gout, pair_in, pair_out, k_offsets, gW2, K, c_out, c_out, max_pairs, algo, stream));
   // bn2 + relu
   B2S_TRY(b2s_bn_backward(z1, y2, tmp_a, n, c_out, stats2, stats2 + c_out, gamma2, 1, 1, tmp_b, dgb2, dgb2 + c_out,
                           bn_counter, bn_ws, bn_bytes, stream));
   // first convolution
-  B2S_TRY(conv_same(tmp_b, W1, tmp_c, n, c_out, c_in, 1, 1, algo, t, conv_ws, conv_bytes, stream));
+  B2S_TRY(conv_same(tmp_b, W1, Wp1, nullptr, tmp_c, n, c_out, c_in, 1, 1, algo, t, conv_ws, conv_bytes, stream));
   B2S_TRY(b2s_conv_wgrad(y1, tmp_b, pair_in, pair_out, k_offsets, gW1, K, c_in, c_out, max_pairs, algo, stream));
-  // bn1 + relu
-  B2S_TRY(b2s_bn_backward(x, y1, tmp_c, n, c_in, stats1, stats1 + c_in, gamma1, 1, 1, gx, dgb1, dgb1 + c_in, bn_counter,
-                          bn_ws, bn_bytes, stream));
-  // shortcut
+  // bn1 + relu, with the gradient that arrives over the shortcut added in the same pass: gout itself (identity
+  // shortcut) or gout @ Wds^T (1x1 convolution; computed first into tmp_a, which is free again by now)
+  const float* shortcut_grad = gout;
   if (Wds != nullptr) {
-    B2S_TRY(b2s_conv_table(gout, Wds, nullptr, nullptr, tmp_c, n, 1, c_out, c_in, 1, 0, algo, conv_ws, conv_bytes, stream));
-    B2S_TRY(add_inplace(gx, tmp_c, n, c_in, stream));
-    return b2s_conv_wgrad(x, gout, ident, ident, ident_koff, gWds, 1, c_in, c_out, n, algo, stream);
+    B2S_TRY(b2s_conv_table(gout, Wds, Wpds, nullptr, nullptr, nullptr, tmp_a, n, 1, c_out, c_in, 1, 0, algo, conv_ws,
+                           conv_bytes, stream));
+    shortcut_grad = tmp_a;
   }
-  return add_inplace(gx, gout, n, c_in, stream);
+  B2S_TRY(b2s_bn_backward_add(x, y1, tmp_c, shortcut_grad, n, c_in, stats1, stats1 + c_in, gamma1, 1, 1, gx, dgb1,
+                              dgb1 + c_in, bn_counter, bn_ws, bn_bytes, stream));
+  if (Wds != nullptr) return b2s_conv_wgrad(x, gout, ident, ident, ident_koff, gWds, 1, c_in, c_out, n, algo, stream);
+  return B2S_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -165,7 +155,7 @@ int b2s_resblock_backward(const float* gout, const float* x, const float* y1, co
 // (harness/models.py: FUSED_UPDOWN) until tools/experiments/fused_updown_check.py has passed.
 // ---------------------------------------------------------------------------------------------------------------
 int b2s_bnconv_forward(const float* x, int64_t n_x, int32_t c_in, int32_t c_out, const float* gamma, const float* beta,
-                       float* rmean, float* rvar, float eps, float mom, const float* W, int32_t mode,
+                       float* rmean, float* rvar, float eps, float mom, const float* W, const float* Wp, int32_t mode,
                        const int32_t* nbr, const uint32_t* tile_mask, const int32_t* pair_in, const int32_t* pair_out,
                        const int32_t* k_offsets, int64_t max_pairs, int64_t n_coarse, int64_t n_fine, int32_t K,
                        float* y, float* stats, float* out, int32_t* bn_counter, int32_t algo, void* ws, size_t ws_bytes,
@@ -188,13 +178,15 @@ int b2s_bnconv_forward(const float* x, int64_t n_x, int32_t c_in, int32_t c_out,
   B2S_TRY(b2s_bn_forward(x, n_x, c_in, eps, mom, rmean, rvar, gamma, beta, 1, y, stats, stats + c_in, bn_counter, bn_ws,
                          bn_bytes, stream));
   if (mode == 0)
-    return b2s_conv_table(y, W, nbr, tile_mask, out, n_coarse, K, c_in, c_out, 0, 0, algo, conv_ws, conv_bytes, stream);
-  return b2s_conv_pairs(y, W, pair_out, pair_in, k_offsets, out, K, c_in, c_out, 0, max_pairs, algo, conv_ws, conv_bytes,
-                        stream);
+    return b2s_conv_table(y, W, Wp, nbr, tile_mask, nullptr, out, n_coarse, K, c_in, c_out, 0, 0, algo, conv_ws,
+                          conv_bytes, stream);
+  return b2s_conv_pairs(y, W, Wp, pair_out, pair_in, k_offsets, out, K, c_in, c_out, 0, max_pairs, algo, conv_ws,
+                        conv_bytes, stream);
 }
 
 int b2s_bnconv_backward(const float* gout, const float* x, const float* y, const float* stats, const float* gamma,
-                        const float* W, int64_t n_x, int32_t c_in, int32_t c_out, int32_t mode, const int32_t* nbr,
+                        const float* W, const float* Wp, int64_t n_x, int32_t c_in, int32_t c_out, int32_t mode,
+                        const int32_t* nbr,
                         const uint32_t* tile_mask, const int32_t* pair_in, const int32_t* pair_out,
                         const int32_t* k_offsets, int64_t max_pairs, int64_t n_coarse, int64_t n_fine, int32_t K,
                         float* gx, float* gW, float* dgb, float* tmp, int32_t* bn_counter, int32_t algo, void* ws,
@@ -215,11 +207,12 @@ int b2s_bnconv_backward(const float* gout, const float* x, const float* y, const
   const size_t conv_bytes = ws_bytes - w.off;
   if (mode == 0) {
     // every fine row has exactly one (coarse row, offset): plain stores, no accumulation
-    B2S_TRY(b2s_conv_pairs(gout, W, pair_out, pair_in, k_offsets, tmp, K, c_out, c_in, 1, max_pairs, algo, conv_ws,
+    B2S_TRY(b2s_conv_pairs(gout, W, Wp, pair_out, pair_in, k_offsets, tmp, K, c_out, c_in, 1, max_pairs, algo, conv_ws,
                            conv_bytes, stream));
     B2S_TRY(b2s_conv_wgrad(y, gout, pair_in, pair_out, k_offsets, gW, K, c_in, c_out, max_pairs, algo, stream));
   } else {
-    B2S_TRY(b2s_conv_table(gout, W, nbr, tile_mask, tmp, n_coarse, K, c_out, c_in, 1, 0, algo, conv_ws, conv_bytes, stream));
+    B2S_TRY(b2s_conv_table(gout, W, Wp, nbr, tile_mask, nullptr, tmp, n_coarse, K, c_out, c_in, 1, 0, algo, conv_ws,
+                           conv_bytes, stream));
     B2S_TRY(b2s_conv_wgrad(y, gout, pair_out, pair_in, k_offsets, gW, K, c_in, c_out, max_pairs, algo, stream));
   }
   return b2s_bn_backward(x, y, tmp, n_x, c_in, stats, stats + c_in, gamma, 1, 1, gx, dgb, dgb + c_in, bn_counter, bn_ws,

@@ -82,7 +82,7 @@ def run_deferred_checks():
 
 
 def deferred_failure_flag(device):
-    """float32 [1] device tensor: 1.0 iff any pending size claim is wrong -- computed on the device, NO host read.
+    """float32 scalar device tensor: 1.0 iff any pending size claim is wrong -- computed on the device, NO host read.
 
     For loops that update weights before the next host read (Trainer.step): hand it to the fused optimizer as
     `found_inf`, which then skips the update on the device, so a wrong claim (rows sliced to a wrong count,
@@ -93,7 +93,7 @@ def deferred_failure_flag(device):
     counts = torch.stack([d for d, _, _ in _DEFERRED])
     expected = torch.tensor([e for _, e, _ in _DEFERRED], dtype=I32).to(device, non_blocking=True)
     bad = (counts[:, 0] != expected) | (counts[:, 1] != 0)
-    return bad.any().to(torch.float32).reshape(1)
+    return bad.any().to(torch.float32).reshape(())
 
 
 def coord_unique(coords, quant=1, assume_unique=False):
@@ -238,33 +238,86 @@ def conv_tc_shape_ok(K, c_in, c_out):
     return 1 <= K <= 32 and c_in >= 16 and c_in % 16 == 0 and c_out >= 16 and c_out % 16 == 0 and c_out <= 256
 
 
+def conv_packed_floats(K, c_in, c_out):
+    """Floats of the packed image of W[K, c_in, c_out] (both orientations), 0 when the tcgen05 path does not take it."""
+    if not (conv_tc_shape_ok(K, c_in, c_out) and conv_tc_shape_ok(K, c_out, c_in)):
+        return 0
+    return 4 * K * c_in * c_out
+
+
+def conv_pack(W, out=None):
+    """b2s_conv_pack: W [K, c_in, c_out] (or [c_in, c_out]) -> the tensor-core operand images, both orientations, one
+    launch.  Pass the result as `packed=` to conv_table / conv_pairs while W is unchanged (once per optimizer step)."""
+    _f32c(W, "W")
+    K, c_in, c_out = (1,) + tuple(W.shape) if W.dim() == 2 else tuple(W.shape)
+    n = conv_packed_floats(K, c_in, c_out)
+    require(n > 0, "conv_pack: shape not taken by the tcgen05 path")
+    if out is None or out.numel() != n:
+        out = torch.empty(n, dtype=torch.float32, device=W.device)
+    check(lib().b2s_conv_pack(ptr(W), ptr(out), K, c_in, c_out, stream()), "conv_pack")
+    return out
+
+
+class PackedWeights:
+    """Per-parameter cache of conv_pack(): re-packed only when the parameter was modified in place (its torch version
+    counter moved: optimizer step, load_state_dict, init) or replaced.  Round 1 re-packed at every product: 170
+    launches per PointGroup step on the critical path of forward and backward."""
+
+    __slots__ = ("ref", "version", "addr", "buf")
+
+    def __init__(self):
+        self.ref, self.version, self.addr, self.buf = None, -1, 0, None
+
+    def __deepcopy__(self, memo):
+        return PackedWeights()
+
+    def get(self, W):
+        if not W.is_cuda:
+            return None
+        if self.ref is W and self.version == W._version and self.addr == W.data_ptr() and self.buf is not None:
+            return self.buf
+        K, c_in, c_out = (1,) + tuple(W.shape) if W.dim() == 2 else tuple(W.shape)
+        if conv_packed_floats(K, c_in, c_out) == 0 or not W.is_contiguous():
+            return None
+        with torch.no_grad():
+            reuse = self.buf if (self.buf is not None and self.buf.device == W.device) else None
+            self.buf = conv_pack(W.detach(), reuse)
+        self.ref, self.version, self.addr = W, W._version, W.data_ptr()
+        return self.buf
+
+
 def conv_table(A, W, nbr, n_out, K, c_in, c_out, w_transposed=False, k_reversed=False, algo=None, tile_mask=None,
-               out_rows=None):
-    """out_rows: nbr / tile_mask are the mask-sorted table of tile_order() and out_rows its row permutation."""
+               out_rows=None, packed=None, add_src=None):
+    """out_rows: nbr / tile_mask are the mask-sorted table of tile_order() and out_rows its row permutation.
+    packed: conv_pack(W) (skips the per-call packing); add_src [n_out, c_out]: residual added to the result."""
     _f32c(A, "A")
     _f32c(W, "W")
+    if add_src is not None:
+        _f32c(add_src, "add_src")
+        require(tuple(add_src.shape) == (n_out, c_out), "add_src must be [n_out, c_out]")
     out = torch.empty((n_out, c_out), dtype=torch.float32, device=A.device)
     ws = _conv_ws(K, c_in, c_out, A.device)
     if out_rows is not None:
-        check(lib().b2s_conv_table_rows(ptr(A), ptr(W), ptr(nbr), ptr(tile_mask), ptr(out_rows), ptr(out), n_out, K,
-                                        c_in, c_out, int(w_transposed), int(k_reversed),
-                                        _default_algo if algo is None else algo, ptr(ws), ws.numel(), stream()),
+        check(lib().b2s_conv_table_rows(ptr(A), ptr(W), ptr(packed), ptr(nbr), ptr(tile_mask), ptr(out_rows),
+                                        ptr(add_src), ptr(out), n_out, K, c_in, c_out, int(w_transposed),
+                                        int(k_reversed), _default_algo if algo is None else algo, ptr(ws), ws.numel(),
+                                        stream()),
               "conv_table_rows")
         return out
-    check(lib().b2s_conv_table(ptr(A), ptr(W), ptr(nbr), ptr(tile_mask), ptr(out), n_out, K, c_in, c_out, int(w_transposed),
-                               int(k_reversed), _default_algo if algo is None else algo, ptr(ws), ws.numel(),
-                               stream()), "conv_table")
+    check(lib().b2s_conv_table(ptr(A), ptr(W), ptr(packed), ptr(nbr), ptr(tile_mask), ptr(add_src), ptr(out), n_out, K,
+                               c_in, c_out, int(w_transposed), int(k_reversed),
+                               _default_algo if algo is None else algo, ptr(ws), ws.numel(), stream()), "conv_table")
     return out
 
 
 def conv_pairs(A, W, src, dst, k_offsets, n_out, K, c_in, c_out, max_pairs, w_transposed=False,
-               zero_init=False, algo=None):
+               zero_init=False, algo=None, packed=None):
     _f32c(A, "A")
     _f32c(W, "W")
     alloc = torch.zeros if zero_init else torch.empty
     out = alloc((n_out, c_out), dtype=torch.float32, device=A.device)
     ws = _conv_ws(K, c_in, c_out, A.device)
-    check(lib().b2s_conv_pairs(ptr(A), ptr(W), ptr(src), ptr(dst), ptr(k_offsets), ptr(out), K, c_in, c_out,
+    check(lib().b2s_conv_pairs(ptr(A), ptr(W), ptr(packed), ptr(src), ptr(dst), ptr(k_offsets), ptr(out), K, c_in, c_out,
                                int(w_transposed), int(max_pairs), _default_algo if algo is None else algo,
                                ptr(ws), ws.numel(), stream()), "conv_pairs")
     return out
