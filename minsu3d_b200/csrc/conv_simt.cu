@@ -190,15 +190,18 @@ __global__ void __launch_bounds__(WG_THREADS)
   const int tg = t % (BG / TG), ta = t / (BG / TG);
   const int a0 = blockIdx.y * BA, g0 = blockIdx.z * BG;
 
+  // offsets first, all threads in parallel; the serial scan then runs out of shared memory (thread 0 walking K + 1
+  // dependent global loads cost ~8 us per launch, a third of the small-map launches' time)
+  for (int k = tid; k <= K; k += WG_THREADS) s_koff[k] = __ldg(k_offsets + k);
+  __syncthreads();
   if (tid == 0) {
     int cum = 0;
     for (int k = 0; k < K; ++k) {
       s_cum[k] = cum;
-      cum += (k_offsets[k + 1] - k_offsets[k] + WG_PC - 1) / WG_PC;
+      cum += (s_koff[k + 1] - s_koff[k] + WG_PC - 1) / WG_PC;
     }
     s_cum[K] = cum;
   }
-  for (int k = tid; k <= K; k += WG_THREADS) s_koff[k] = k_offsets[k];
   __syncthreads();
   const int total_chunks = s_cum[K];
   const int per = (total_chunks + gridDim.x - 1) / gridDim.x;

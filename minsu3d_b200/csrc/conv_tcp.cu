@@ -13,8 +13,20 @@
 //     allocation live for the whole kernel, pipeline state (stage / slot / phase) carries over from item to item.
 //   * Weights stay RESIDENT in shared memory when the whole layer fits (16 -> 16: 27 slabs x 2 KB): one bulk copy per
 //     slab per CTA instead of one per slab per tile; otherwise the ring streams them as before.
-//   * The next item's gather indices are prefetched by the TMA engine (one 13.8 KB bulk copy) into the second half
-//     of a double buffer while the producers still work on the current item.
+//   * The next items' gather indices are prefetched by the TMA engine (one 13.8 KB bulk copy) into a double buffer,
+//     requested by producer warp 0 the moment a buffer is free.
+//   * Gather staging.  Default: three register slots per producer thread (two slabs of LDG.256 in flight), the next
+//     item's first loads issued before the accumulator is drained.  The round-2 ncu capture of this kernel on the
+//     level-0 map (profiles/r02_conv_tcp_ncu.txt) shows a latency-bound gather -- 41 % of the warp samples wait on the
+//     first use of a gathered register, 0.43 eligible warps per scheduler, issue slots 32 %, L2 at 44 % of its
+//     throughput cap -- and two remedies were built and MEASURED SLOWER, so they are not the default:
+//       - ASYNC (B2S_TC_ASYNC=1, kept as an experiment switch): every producer thread copies its neighbour rows with
+//         cp.async.cg into a thread-private, XOR-swizzled row of a 5-deep shared-memory ring (five slabs in flight, no
+//         registers, cursor runs ahead across item boundaries) and reads it back with conflict-free LDS.128.  cp.async
+//         moves at most 16 bytes per lane: 2.8x the L1TEX wavefronts of LDG.256 (6.6 M vs 2.4 M per launch), L1TEX
+//         65 % busy -- 16->16 level 0: 64 us vs 50 us, 32->32 level 1: 44 us vs 37 us.
+//       - lane pairs that fetch the two halves of a row in one instruction and swap them with shuffles: wavefronts
+//         halve (1.28 M) but the 8 SHFL + 24 SEL per slab cost more than they save: 56-60 us vs 50 us.
 //   * Two accumulators in TMEM: the MMA warp starts the next item while the producer warps drain the previous
 //     accumulator (tcgen05.ld -> global); the producers issue the next item's first gathers BEFORE that epilogue.
 //   * The residual add of the MinkUNet block (common.py:48 `x += shortcut`) is folded into the epilogue.
@@ -33,10 +45,12 @@
 
 namespace b2s {
 
-__device__ float g_zero_row_p[256];  // what a missing neighbour reads (keeps the gather loop branch-free)
+__device__ float g_zero_row_p[256];  // register mode: what a missing neighbour reads (keeps the gather loop branch-free)
 
 constexpr int TCP_MAX_SB = 64;
 constexpr int TCP_MAX_S = 6;
+constexpr int TCP_DEPTH = 5;            // ASYNC: slabs of cp.async copies in flight per thread
+constexpr int TCP_GSTAGE = TC_BM * 64;  // bytes of one gather stage (128 rows x 16 channels)
 
 struct TcpArgs {
   const float* A;
@@ -56,7 +70,16 @@ struct TcpArgs {
   int idx_bulk;               // nbr base is 16-byte aligned: index tiles are moved with cp.async.bulk
 };
 
-template <int NSPLIT>
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int NSPLIT, bool ASYNC>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -69,7 +92,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
   const int b_slab = a.c_out * 64;
   const int b_slot = NB * b_slab;
   const int nc = a.c_in >> 4;
-  // shared memory: [SB weight slots][barriers][tmem ptr][index tile 0][index tile 1]
+  // shared memory: [SB weight slots][barriers][tmem ptr][index tile 0][index tile 1][ASYNC: gather ring]
   const uint32_t bar0 = base + (uint32_t)SB * b_slot;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
@@ -86,6 +109,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
   const int idx_tile_ints = TC_BM * K;
   int32_t* s_idx0 = (int32_t*)(sm + idx_off);
   const uint32_t s_idx0_u32 = base + (uint32_t)idx_off;
+  const bool has_idx = a.idx != nullptr;
+  const size_t gat_off = (idx_off + (has_idx ? (size_t)2 * idx_tile_ints * 4 : 0) + 127) & ~(size_t)127;
 
   // ---- one-time prologue ---------------------------------------------------------------------
   if (tid < nbar) {
@@ -101,10 +126,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const bool has_idx = a.idx != nullptr;
   const uint32_t all_mask = has_idx ? (K >= 32 ? 0xffffffffu : ((1u << K) - 1u)) : 1u;
+  const int G = (int)gridDim.x;
 
-  // mask of the offsets work item `item` covers: the tile's active offsets, or this part's share of them
+  // mask of the offsets work item `item` covers: the tile's active offsets, restricted to this part's range
   auto item_mask = [&](int item) -> uint32_t {
     const int tile = a.splits > 1 ? item / a.splits : item;
     uint32_t kmask = (has_idx && a.tile_mask != nullptr) ? __ldg(a.tile_mask + tile) & all_mask : all_mask;
@@ -129,32 +154,96 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
     const uint32_t d_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
     int st_s = 0;
     uint32_t st_ph = 0;
-    // per-item gather state
-    const int32_t* my_idx = nullptr;
-    int ident_row = -1;
-    uint32_t km = 0;
-    int lk = 0, lc = 0;
-    float ra[16], rb[16], rc[16];
-    auto load_next = [&](float (&dst)[16]) {
-      const bool adv = (lc == 0);
-      const int kn = __ffs(km) - 1;
-      lk = adv ? kn : lk;
-      km = adv ? (km & (km - 1)) : km;
-      const int g = has_idx ? my_idx[lk] : ident_row;
-      const float* p = (g >= 0) ? Ag + ((int64_t)g * c_in + lc * 16) : g_zero_row_p;
-      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=f"(dst[0]), "=f"(dst[1]), "=f"(dst[2]), "=f"(dst[3]), "=f"(dst[4]), "=f"(dst[5]), "=f"(dst[6]),
-                     "=f"(dst[7])
-                   : "l"(p));
-      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=f"(dst[8]), "=f"(dst[9]), "=f"(dst[10]), "=f"(dst[11]), "=f"(dst[12]), "=f"(dst[13]),
-                     "=f"(dst[14]), "=f"(dst[15])
-                   : "l"(p + 8));
-      lc = (lc + 1 == nc) ? 0 : lc + 1;
+
+    // ---- index tiles: requested by warp 0 as soon as a buffer is free (local item number j -> buffer j & 1) -------
+    auto load_idx = [&](int item, int j) {  // warp 0 only, converged
+      const int b = j & 1;
+      const int tile = a.splits > 1 ? item / a.splits : item;
+      const int64_t row0 = (int64_t)tile * TC_BM;
+      const int rows = (int)min((int64_t)TC_BM, a.n_out - row0);
+      const int32_t* src = a.idx + row0 * K;
+      int32_t* dst = s_idx0 + b * idx_tile_ints;
+      const uint32_t bytes = (uint32_t)rows * (uint32_t)K * 4u;
+      if (a.idx_bulk && rows == TC_BM) {
+        if (elect_one()) {
+          mbar_arrive_expect_tx(ifull_bar(b), bytes);
+          bulk_g2s(s_idx0_u32 + (uint32_t)(b * idx_tile_ints) * 4u, src, bytes, ifull_bar(b));
+        }
+        __syncwarp();
+      } else {  // last (partial) tile or unaligned table: plain copies, rows past the end hold -1
+        const int total = rows * K;
+        for (int e = lane; e < total; e += 32) dst[e] = __ldg(src + e);
+        for (int e = total + lane; e < idx_tile_ints; e += 32) dst[e] = -1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ifull_bar(b));
+      }
     };
-    auto store_slab = [&](const float (&src)[16]) {
-      mbar_wait(empty_bar(st_s), st_ph ^ 1u);
-      tc_fence_after();
+    // the gather cursor has read every index of local item j: release the buffer; warp 0 refills it for item j + 2
+    auto release_idx = [&](int item, int j) {
+      if (!has_idx) return;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(iempty_bar(j & 1));
+      if (warp == 0) {
+        const int nxt = item + 2 * G;
+        if (nxt < a.n_items) {
+          mbar_wait(iempty_bar(j & 1), (uint32_t)(j >> 1) & 1u);  // the other three producer warps are at most one slab behind
+          load_idx(nxt, j + 2);
+        }
+      }
+    };
+    if (has_idx && warp == 0) {
+      if ((int)blockIdx.x < a.n_items) load_idx(blockIdx.x, 0);
+      if ((int)blockIdx.x + G < a.n_items) load_idx(blockIdx.x + G, 1);
+    }
+
+    // ---- gather cursor: (item, offset, channel chunk) of the next slab to fetch ----------------------------
+    int g_item = blockIdx.x, g_it = 0, g_rem = 0;
+    bool g_valid = false;
+    uint32_t g_km = 0, g_next_mask = (g_item < a.n_items) ? item_mask(g_item) : 0u;
+    int g_lk = 0, g_lc = 0, g_ident = -1;
+    const int32_t* g_idx = nullptr;
+    auto gather_begin = [&](int item) {
+      g_item = item;
+      const int tile = a.splits > 1 ? item / a.splits : item;
+      const int64_t row0 = (int64_t)tile * TC_BM;
+      const int rows = (int)min((int64_t)TC_BM, a.n_out - row0);
+      g_km = g_next_mask;
+      if (item + G < a.n_items) g_next_mask = item_mask(item + G);  // one item ahead: latency hidden behind this item
+      g_rem = __popc(g_km) * nc;
+      if (has_idx) {
+        mbar_wait(ifull_bar(g_it & 1), (uint32_t)(g_it >> 1) & 1u);
+        g_idx = s_idx0 + (g_it & 1) * idx_tile_ints + r * K;  // rows past the end of the table hold -1
+      } else {
+        g_ident = (r < rows) ? (int)(row0 + r) : -1;
+      }
+      g_lk = 0;
+      g_lc = 0;
+      ++g_it;
+      g_valid = true;
+    };
+    // moves the cursor to an item that still has slabs (releasing finished items' index tiles); false = no work left
+    auto gather_advance = [&]() -> bool {
+      while (g_valid && g_rem == 0) {
+        release_idx(g_item, g_it - 1);
+        if (g_item + G < a.n_items) gather_begin(g_item + G);
+        else g_valid = false;
+      }
+      return g_valid;
+    };
+    // gather index + source pointer of the cursor's slab, then step the cursor
+    auto gather_next = [&](int& g, const float*& p) {
+      const bool adv = (g_lc == 0);
+      const int kn = __ffs(g_km) - 1;
+      g_lk = adv ? kn : g_lk;
+      g_km = adv ? (g_km & (g_km - 1)) : g_km;
+      g = has_idx ? g_idx[g_lk] : g_ident;
+      p = Ag + ((int64_t)max(g, 0) * c_in + g_lc * 16);
+      g_lc = (g_lc + 1 == nc) ? 0 : g_lc + 1;
+      --g_rem;
+    };
+
+    // ---- TMEM store of one gathered slab (thread = tile row = TMEM lane) ---------------------------------
+    auto split_store = [&](const float (&src)[16], auto&& between) {
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -166,85 +255,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
           hi[j] = __float_as_uint(src[j]);
         }
       }
+      between();  // ASYNC: refill of the ring slot just read (its values are in hi / lo now)
+      mbar_wait(empty_bar(st_s), st_ph ^ 1u);
+      tc_fence_after();
       const uint32_t col = a_lane + (uint32_t)(st_s * A_COLS);
       tmem_st16(col, hi);
       if (NSPLIT == 3) tmem_st16(col + 16, lo);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(st_s));
+      if (lane == 0) mbar_arrive(full_bar(st_s));  // 4 arrivals per slab instead of 128 serialised ones
       const bool wrap = (st_s + 1 == S);
       st_s = wrap ? 0 : st_s + 1;
       st_ph ^= wrap ? 1u : 0u;
     };
-    // item bookkeeping
-    int it = 0;      // items this CTA has started
-    int n_acc = 0;   // items with at least one slab so far (accumulator uses)
-    int item = blockIdx.x;
-    int T = 0, tile = 0, rows = 0;
-    int64_t row0 = 0;
-    int orow_perm = -1;
-    uint32_t next_mask = (item < a.n_items) ? item_mask(item) : 0u;  // mask of the item that begins next
-    auto begin_item = [&](int new_item) {
-      item = new_item;
-      tile = a.splits > 1 ? item / a.splits : item;
-      row0 = (int64_t)tile * TC_BM;
-      rows = (int)min((int64_t)TC_BM, a.n_out - row0);
-      const uint32_t kmask = next_mask;
-      const int after = item + (int)gridDim.x;
-      if (after < a.n_items) next_mask = item_mask(after);  // one item ahead: its latency hides behind this item
-      T = __popc(kmask) * nc;
-      orow_perm = (a.out_rows != nullptr && r < rows) ? __ldg(a.out_rows + row0 + r) : -1;
-      if (has_idx) {
-        const int b = it & 1;
-        mbar_wait(ifull_bar(b), (uint32_t)(it >> 1) & 1u);
-        // rows past the end of the table (last tile only) hold -1 in the index tile: they gather the zero row
-        my_idx = s_idx0 + b * idx_tile_ints + r * K;
-      } else {
-        ident_row = (r < rows) ? (int)(row0 + r) : -1;
-      }
-      km = kmask;
-      lk = 0;
-      lc = 0;
-      ++it;
-    };
-    if (item < a.n_items) {
-      begin_item(item);
-      if (T > 0) load_next(ra);
-      if (T > 1) load_next(rb);
-    }
-    while (item < a.n_items) {
-      for (int t = 0; t < T; t += 3) {
-        if (t + 2 < T) load_next(rc);
-        store_slab(ra);
-        if (t + 3 < T) load_next(ra);
-        if (t + 1 < T) store_slab(rb);
-        if (t + 4 < T) load_next(rb);
-        if (t + 2 < T) store_slab(rc);
-      }
-      // every index of this item has been read: hand the index tile back to the loader
-      if (has_idx) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(iempty_bar((it - 1) & 1));
-      }
-      // epilogue bookkeeping of the item just gathered
-      const int e_T = T;
-      const int e_part = a.splits > 1 ? item - tile * a.splits : 0;
-      const int64_t e_orow = (r < rows) ? (orow_perm >= 0 ? (int64_t)orow_perm : row0 + r) : -1;
-      const int e_ab = (e_T > 0) ? (n_acc % a.acc_bufs) : 0;
-      const uint32_t e_ph = (uint32_t)(n_acc / a.acc_bufs) & 1u;
-      if (e_T > 0) ++n_acc;
-      // start the next item's gathers before draining the accumulator
-      const int next = item + (int)gridDim.x;
-      const bool has_next = next < a.n_items;
-      if (has_next) {
-        begin_item(next);
-        if (T > 0) load_next(ra);
-        if (T > 1) load_next(rb);
-      } else {
-        item = next;
-      }
-      // ---- epilogue: TMEM -> registers -> (+ residual) -> global --------------------------------
+
+    // ---- epilogue: TMEM -> registers -> (+ residual) -> global ----------------------------------------------
+    auto epilogue = [&](int e_T, int e_part, int64_t e_orow, int e_ab, uint32_t e_ph) {
       if (e_T > 0) {
         mbar_wait(tfull_bar(e_ab), e_ph);
         tc_fence_after();
@@ -282,6 +309,117 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
         __syncwarp();
         if (lane == 0) mbar_arrive(aempty_bar(e_ab));
       }
+    };
+
+    // ---- consume cursor: items in order, T slabs each --------------------------------------------------------
+    int n_acc = 0;  // items with at least one slab so far (accumulator uses)
+    uint32_t c_next_mask = ((int)blockIdx.x < a.n_items) ? item_mask(blockIdx.x) : 0u;
+    if ((int)blockIdx.x < a.n_items) gather_begin(blockIdx.x);
+
+    if constexpr (ASYNC) {
+      // ring slot of slab number q (counted over the CTA's whole slab stream) = q % TCP_DEPTH; row r of a slot is
+      // thread-private: 64 bytes, its four 16-byte chunks XOR-swizzled with (r >> 1) & 3 (conflict-free LDS.128)
+      const uint32_t my_row = base + (uint32_t)gat_off + (uint32_t)r * 64u;
+      const uint32_t sw = (uint32_t)((r >> 1) & 3);
+      auto issue = [&](int slot) {  // one commit group per call, empty when the stream has ended
+        if (gather_advance()) {
+          int g;
+          const float* p;
+          gather_next(g, p);
+          const uint32_t nb = (g >= 0) ? 16u : 0u;  // missing neighbour: zero-fill, nothing is read
+          const uint32_t dst = my_row + (uint32_t)slot * TCP_GSTAGE;
+#pragma unroll
+          for (uint32_t q = 0; q < 4; ++q) cp_async16(dst + ((q ^ sw) << 4), p + 4 * q, nb);
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int d = 0; d < TCP_DEPTH; ++d) issue(d);
+      int slot = 0;
+      for (int item = blockIdx.x; item < a.n_items; item += G) {
+        const uint32_t kmask = c_next_mask;
+        if (item + G < a.n_items) c_next_mask = item_mask(item + G);
+        const int T = __popc(kmask) * nc;
+        const int tile = a.splits > 1 ? item / a.splits : item;
+        const int64_t row0 = (int64_t)tile * TC_BM;
+        const int rows = (int)min((int64_t)TC_BM, a.n_out - row0);
+        const int orow_perm = (a.out_rows != nullptr && r < rows) ? __ldg(a.out_rows + row0 + r) : -1;
+        for (int t = 0; t < T; ++t) {
+          cp_async_wait<TCP_DEPTH - 1>();  // the oldest group (this slab) has landed
+          float src[16];
+          const uint32_t row = my_row + (uint32_t)slot * TCP_GSTAGE;
+#pragma unroll
+          for (uint32_t q = 0; q < 4; ++q)
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(src[4 * q]), "=f"(src[4 * q + 1]), "=f"(src[4 * q + 2]), "=f"(src[4 * q + 3])
+                         : "r"(row + ((q ^ sw) << 4)));
+          const int cur = slot;
+          split_store(src, [&]() { issue(cur); });
+          slot = (slot + 1 == TCP_DEPTH) ? 0 : slot + 1;
+        }
+        const int e_ab = (T > 0) ? (n_acc % a.acc_bufs) : 0;
+        const uint32_t e_ph = (uint32_t)(n_acc / a.acc_bufs) & 1u;
+        if (T > 0) ++n_acc;
+        const int64_t e_orow = (r < rows) ? (orow_perm >= 0 ? (int64_t)orow_perm : row0 + r) : -1;
+        epilogue(T, a.splits > 1 ? item - tile * a.splits : 0, e_orow, e_ab, e_ph);
+      }
+      cp_async_wait<0>();
+    } else {
+      // register mode (fallback when the gather ring does not fit): three register slots rotate, two slabs of loads
+      // in flight per thread; the next item's first loads are issued before the accumulator is drained
+      float ra[16], rb[16], rc[16];
+      auto load_next = [&](float (&dst)[16]) {
+        int g;
+        const float* p;
+        gather_next(g, p);
+        p = (g >= 0) ? p : g_zero_row_p;
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(dst[0]), "=f"(dst[1]), "=f"(dst[2]), "=f"(dst[3]), "=f"(dst[4]), "=f"(dst[5]), "=f"(dst[6]),
+                       "=f"(dst[7])
+                     : "l"(p));
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(dst[8]), "=f"(dst[9]), "=f"(dst[10]), "=f"(dst[11]), "=f"(dst[12]), "=f"(dst[13]),
+                       "=f"(dst[14]), "=f"(dst[15])
+                     : "l"(p + 8));
+      };
+      auto nothing = []() {};
+      int T = 0;
+      for (int item = blockIdx.x; item < a.n_items;) {
+        if (item == (int)blockIdx.x) {  // first item: nothing is in flight yet
+          T = g_rem;
+          if (T > 0) load_next(ra);
+          if (T > 1) load_next(rb);
+        }
+        const int tile = a.splits > 1 ? item / a.splits : item;
+        const int64_t row0 = (int64_t)tile * TC_BM;
+        const int rows = (int)min((int64_t)TC_BM, a.n_out - row0);
+        const int orow_perm = (a.out_rows != nullptr && r < rows) ? __ldg(a.out_rows + row0 + r) : -1;
+        for (int t = 0; t < T; t += 3) {
+          if (t + 2 < T) load_next(rc);
+          split_store(ra, nothing);
+          if (t + 3 < T) load_next(ra);
+          if (t + 1 < T) split_store(rb, nothing);
+          if (t + 4 < T) load_next(rb);
+          if (t + 2 < T) split_store(rc, nothing);
+        }
+        const int e_T = T;
+        const int e_ab = (e_T > 0) ? (n_acc % a.acc_bufs) : 0;
+        const uint32_t e_ph = (uint32_t)(n_acc / a.acc_bufs) & 1u;
+        if (e_T > 0) ++n_acc;
+        const int64_t e_orow = (r < rows) ? (orow_perm >= 0 ? (int64_t)orow_perm : row0 + r) : -1;
+        const int e_part = a.splits > 1 ? item - tile * a.splits : 0;
+        // every index of this item has been read: release its tile, then start the next item's gathers before
+        // draining the accumulator
+        release_idx(item, g_it - 1);
+        item += G;
+        if (item < a.n_items) {
+          gather_begin(item);
+          T = g_rem;
+          if (T > 0) load_next(ra);
+          if (T > 1) load_next(rb);
+        }
+        epilogue(e_T, e_part, e_orow, e_ab, e_ph);
+      }
     }
     tc_fence_before();
   } else if (warp == 4) {
@@ -290,9 +428,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
     int s = 0, j = 0, n_acc = 0;
     uint32_t ph = 0, bph = 0;
     uint32_t next_mask = ((int)blockIdx.x < a.n_items) ? item_mask(blockIdx.x) : 0u;
-    for (int item = blockIdx.x; item < a.n_items; item += (int)gridDim.x) {
+    for (int item = blockIdx.x; item < a.n_items; item += G) {
       uint32_t km = next_mask;
-      if (item + (int)gridDim.x < a.n_items) next_mask = item_mask(item + (int)gridDim.x);
+      if (item + G < a.n_items) next_mask = item_mask(item + G);
       const int T = __popc(km) * nc;
       if (T == 0) continue;
       const int ab = n_acc % a.acc_bufs;
@@ -347,7 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
       }
     }
   } else {
-    // =========================== TMA loader: weights + index tiles ============================
+    // =========================== TMA loader: weight slabs =====================================
     auto load_weight = [&](int slot, int kw, int c) {
       const uint32_t b_hi = base + (uint32_t)slot * b_slot;
       const float* src = a.Bp + ((int64_t)kw * nc + c) * (int64_t)(a.c_out * 16);
@@ -355,36 +493,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
       bulk_g2s(b_hi, src, (uint32_t)b_slab, bfull_bar(slot));
       if (NSPLIT == 3) bulk_g2s(b_hi + b_slab, src + a.bp_half, (uint32_t)b_slab, bfull_bar(slot));
     };
-    // index tile of work item `item` into buffer (it & 1); rows past the end of the table are filled with -1
-    auto load_idx = [&](int item, int it) {
-      const int b = it & 1;
-      if (it >= 2) mbar_wait(iempty_bar(b), (uint32_t)((it >> 1) - 1) & 1u);
-      const int tile = a.splits > 1 ? item / a.splits : item;
-      const int64_t row0 = (int64_t)tile * TC_BM;
-      const int rows = (int)min((int64_t)TC_BM, a.n_out - row0);
-      const int32_t* src = a.idx + row0 * K;
-      int32_t* dst = s_idx0 + b * idx_tile_ints;
-      const uint32_t bytes = (uint32_t)rows * (uint32_t)K * 4u;
-      if (a.idx_bulk && rows == TC_BM) {
-        if (elect_one()) {
-          mbar_arrive_expect_tx(ifull_bar(b), bytes);
-          bulk_g2s(s_idx0_u32 + (uint32_t)(b * idx_tile_ints) * 4u, src, bytes, ifull_bar(b));
-        }
-        __syncwarp();
-      } else {
-        const int total = rows * K;
-        for (int e = lane; e < total; e += 32) dst[e] = __ldg(src + e);
-        for (int e = total + lane; e < idx_tile_ints; e += 32) dst[e] = -1;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ifull_bar(b));
-      }
-    };
-    int it = 0;
     const int first = blockIdx.x;
-    if (first < a.n_items) {
-      if (has_idx) load_idx(first, 0);
-      if (a.resident) {
-        // every slab of the layer, slot = (tile offset k, chunk c); source offset honours k_reversed
+    if (a.resident) {
+      if (first < a.n_items) {
+        // every slab of the layer once per CTA, slot = (tile offset k, chunk c); the source honours k_reversed
         for (int k = 0; k < K; ++k) {
           const int kw = a.k_reversed ? (K - 1 - k) : k;
           for (int c = 0; c < nc; ++c) {
@@ -392,50 +504,38 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
             __syncwarp();
           }
         }
+        // a CTA must not exit with bulk copies in flight: slabs its items never touch are awaited here
+        for (int slot = 0; slot < K * nc; ++slot) mbar_wait(bfull_bar(slot), 0u);
       }
-    }
-    int j = 0;
-    uint32_t bph = 0;
-    long long issued = 0;  // weight slabs issued so far (streaming mode): the first SB need no bempty wait
-    uint32_t next_mask = (first < a.n_items && !a.resident) ? item_mask(first) : 0u;
-    for (int item = first; item < a.n_items; item += (int)gridDim.x, ++it) {
-      const int next = item + (int)gridDim.x;
-      const bool want_idx = has_idx && next < a.n_items;
-      if (a.resident) {
-        if (want_idx) load_idx(next, it + 1);
-        continue;
-      }
-      uint32_t km = next_mask;
-      if (next < a.n_items) next_mask = item_mask(next);
-      const int T = __popc(km) * nc;
-      // the next index tile is requested after the first half ring of this item's weights: early enough to land
-      // before the producers need it, late enough that this item's first weights are not held up by the wait for
-      // the index buffer (released when the producers finish gathering the previous item)
-      const int idx_at = min(T, SB) / 2;
-      int k = -1, c = nc;
-      for (int t = 0; t < T; ++t) {
-        if (t == idx_at && want_idx) load_idx(next, it + 1);
-        if (c == nc) {
-          k = __ffs(km) - 1;
-          km &= km - 1;
-          c = 0;
-        }
-        const int kw = a.k_reversed ? (K - 1 - k) : k;
-        if (issued >= SB) mbar_wait(bempty_bar(j), bph ^ 1u);
-        if (elect_one()) load_weight(j, kw, c);
-        __syncwarp();
-        ++issued;
-        ++c;
-        if (++j == SB) {
-          j = 0;
-          bph ^= 1u;
+    } else {
+      int j = 0;
+      uint32_t bph = 0;
+      long long issued = 0;  // the first SB slabs need no bempty wait
+      uint32_t next_mask = (first < a.n_items) ? item_mask(first) : 0u;
+      for (int item = first; item < a.n_items; item += G) {
+        uint32_t km = next_mask;
+        if (item + G < a.n_items) next_mask = item_mask(item + G);
+        const int T = __popc(km) * nc;
+        int k = -1, c = nc;
+        for (int t = 0; t < T; ++t) {
+          if (c == nc) {
+            k = __ffs(km) - 1;
+            km &= km - 1;
+            c = 0;
+          }
+          const int kw = a.k_reversed ? (K - 1 - k) : k;
+          if (issued >= SB) mbar_wait(bempty_bar(j), bph ^ 1u);
+          if (elect_one()) load_weight(j, kw, c);
+          __syncwarp();
+          ++issued;
+          ++c;
+          if (++j == SB) {
+            j = 0;
+            bph ^= 1u;
+          }
         }
       }
-      if (T <= idx_at && want_idx) load_idx(next, it + 1);  // T == 0
     }
-    // a CTA must not exit with bulk copies in flight: resident slabs its items never touched are awaited here
-    if (a.resident && first < a.n_items)
-      for (int slot = 0; slot < K * nc; ++slot) mbar_wait(bfull_bar(slot), 0u);
   }
   __syncthreads();
   if (warp == 4) {
@@ -502,12 +602,33 @@ static int launch_tcp(TcpArgs a, void* split_ws, float* final_out, const float* 
   a.a_col0 = ab * a.c_out;
   a.tmem_cols = bucket;
   const int ctas_per_sm = bucket > 256 ? 1 : 2;
-  // ---- weights: resident if every slab fits in 72 KB (and <= 64 slots), else a streaming ring of <= 64 KB ------
+  // ---- shared memory plan: [weights][barriers][2 index tiles][ASYNC: gather ring of TCP_DEPTH x 8 KB] ------------
+  // budget per CTA: 112 KB when two CTAs share an SM, 220 KB when the TMEM allocation allows only one
   const int total_slabs = a.K * (a.c_in / 16);
-  const bool resident = total_slabs <= TCP_MAX_SB && (size_t)total_slabs * b_slot <= 72 * 1024;
+  const size_t budget = (size_t)(ctas_per_sm == 2 ? 112 : 220) * 1024;
+  const size_t idx_bytes = a.idx != nullptr ? (size_t)2 * TC_BM * a.K * 4 : 0;
+  const size_t fixed = 1024 /*align slack*/ + 8 * (size_t)(2 * TCP_MAX_S + 8) + 32 + idx_bytes + 64 + 128;
+  auto plan = [&](size_t extra, bool* resident, int* sb) {  // weights in what is left after `extra`; false = does not fit
+    if (fixed + extra + 2 * (size_t)b_slot + 64 > budget) return false;
+    const size_t room = budget - fixed - extra;
+    // every slab costs its slot + two barriers
+    const int cap_slots = (int)std::min<size_t>(TCP_MAX_SB, room / ((size_t)b_slot + 16));
+    *resident = total_slabs <= cap_slots;
+    *sb = *resident ? total_slabs : std::min(total_slabs, cap_slots);
+    return *resident || *sb >= 2;
+  };
+  bool resident = false, async = tcp_env("B2S_TC_ASYNC", 0) != 0;
+  int sb = 2;
+  if (async) {
+    async = plan((size_t)TCP_DEPTH * TCP_GSTAGE, &resident, &sb) && (resident || sb >= 4);
+  }
+  if (!async && !plan(0, &resident, &sb)) {
+    set_error("conv_tcp: shared memory plan failed");
+    return B2S_E_INVALID;
+  }
+  if (!resident) sb = std::max(2, std::min(sb, tcp_env("B2S_TC_SB", TCP_MAX_SB)));
   a.resident = resident ? 1 : 0;
-  a.sb = resident ? total_slabs : std::max(2, std::min(std::min(total_slabs, TCP_MAX_SB), (64 * 1024) / b_slot));
-  if (!resident) a.sb = std::max(2, std::min(a.sb, tcp_env("B2S_TC_SB", TCP_MAX_SB)));
+  a.sb = sb;
   // ---- work items -------------------------------------------------------------------------------------
   a.n_tiles = (int)cdiv(a.n_out, TC_BM);
   const int slots = sm_count() * ctas_per_sm;
@@ -532,15 +653,15 @@ static int launch_tcp(TcpArgs a, void* split_ws, float* final_out, const float* 
     a.add_src = add_src;
   }
   const int nbar = 2 * S + 2 * a.sb + 8;
-  size_t smem = 1024 /*align slack*/ + (size_t)a.sb * b_slot + 8 * (size_t)nbar + 32 +
-                (a.idx != nullptr ? (size_t)2 * TC_BM * a.K * 4 : 0) + 64;
+  size_t smem = 1024 /*align slack*/ + (size_t)a.sb * b_slot + 8 * (size_t)nbar + 32 + idx_bytes + 64 + 128 +
+                (async ? (size_t)TCP_DEPTH * TCP_GSTAGE : 0);
   if (ctas_per_sm == 1) smem = std::max(smem, (size_t)120 * 1024);  // 512 TMEM columns: keep a second CTA off the SM
-  auto kern = conv_tcp_kernel<NSPLIT>;
-  static size_t configured[B2S_MAX_DEVICES] = {0};
+  auto kern = async ? conv_tcp_kernel<NSPLIT, true> : conv_tcp_kernel<NSPLIT, false>;
+  static size_t configured[B2S_MAX_DEVICES][2] = {};
   const int dev = current_device();
-  if (smem > configured[dev]) {
+  if (smem > configured[dev][async]) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured[dev] = smem;
+    configured[dev][async] = smem;
   }
   const int grid = std::min(a.n_items, slots);
   kern<<<grid, TC_THREADS, smem, stream>>>(a);

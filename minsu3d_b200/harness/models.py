@@ -107,8 +107,10 @@ class Backbone(nn.Module):
     def forward(self, voxel_features, voxel_coordinates, v2p_map, level_sizes=None):
         # the loader's voxels are unique by construction (sparse_quantize) and it reports the level sizes: no host
         # read of device counts in the whole backbone, the host keeps enqueuing while the GPU finishes the last step
+        # (uniqueness is the loader's contract -- the voxels come out of sparse_quantize, general_dataset.py:159 -- and is
+        # validated on the device; level sizes are optional loader metadata, bench.py --size-hints)
         x = ME.SparseTensor(features=voxel_features, coordinates=voxel_coordinates,
-                            coordinates_unique=level_sizes is not None, level_sizes=level_sizes)
+                            coordinates_unique=ASYNC_SIZES, level_sizes=level_sizes)
         unet_out = self.unet(x)
         point_features = ops.devoxelize(unet_out.features, v2p_map)  # == features[v2p_map], backbone.py:40
         return {"point_features": point_features,

@@ -38,16 +38,15 @@ def reserve_device_pool(device, gigabytes):
 
 
 class Trainer:
-    def __init__(self, cfg: models.Config, device, bucket_mb=8.0, seed=123, reserve_gb=0.0, overlap_allreduce=False):
+    def __init__(self, cfg: models.Config, device, bucket_mb=8.0, seed=123, reserve_gb=0.0, overlap_allreduce=True):
         torch.manual_seed(seed)  # config/config.yaml:17
         self.cfg = cfg
         self.device = torch.device(device)
         reserve_device_pool(self.device, reserve_gb)
         self.model = models.build_model(cfg).to(self.device)
         self.model.train()
-        # NVLink: pack after backward (dp.py) -- the all-reduce is far cheaper than per-parameter hooks
-        self.bucketer = dp.GradBucketer(self.model.parameters(), bucket_mb=bucket_mb,
-                                        overlap=(self.device.type != "cuda" or overlap_allreduce))
+        # buckets are packed and all-reduced from inside backward as they complete (dp.py)
+        self.bucketer = dp.GradBucketer(self.model.parameters(), bucket_mb=bucket_mb, overlap=overlap_allreduce)
         # same update rule as the reference's torch.optim.Adam; the fused multi-tensor implementation keeps the
         # host cost of the ~200-parameter step at a few launches (the default foreach path costs ~5 ms of Python)
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr, fused=(self.device.type == "cuda"))

@@ -258,15 +258,34 @@ def conv_pack(W, out=None):
     return out
 
 
-class PackedWeights:
-    """Per-parameter cache of conv_pack(): re-packed only when the parameter was modified in place (its torch version
-    counter moved: optimizer step, load_state_dict, init) or replaced.  Round 1 re-packed at every product: 170
-    launches per PointGroup step on the critical path of forward and backward."""
+# Every torch optimizer step invalidates the packed images: the fused (multi-tensor CUDA) optimizers update the
+# parameters WITHOUT moving their version counters (torch.optim.Adam(fused=True): `_version` stays put), so the
+# version alone cannot be trusted.  The hook is global (torch.optim.optimizer), cheap (one integer), and registered
+# once at import.  Writers that bypass both mechanisms (raw kernels on `data_ptr()`) must call invalidate_packed().
+_PACK_EPOCH = [0]
 
-    __slots__ = ("ref", "version", "addr", "buf")
+
+def invalidate_packed(*_args, **_kwargs):
+    _PACK_EPOCH[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook
+    _register_step_hook(invalidate_packed)
+except ImportError:  # pragma: no cover -- torch < 2.0
+    _register_step_hook = None
+
+
+class PackedWeights:
+    """Per-parameter cache of conv_pack(): re-packed when the parameter was modified in place (its torch version
+    counter moved: load_state_dict, init, in-place ops), replaced or moved, or when ANY optimizer has stepped since
+    (see _PACK_EPOCH).  Round 1 re-packed at every product: 170 launches per PointGroup step on the critical path
+    of forward and backward."""
+
+    __slots__ = ("ref", "version", "addr", "epoch", "buf")
 
     def __init__(self):
-        self.ref, self.version, self.addr, self.buf = None, -1, 0, None
+        self.ref, self.version, self.addr, self.epoch, self.buf = None, -1, 0, -1, None
 
     def __deepcopy__(self, memo):
         return PackedWeights()
@@ -274,7 +293,8 @@ class PackedWeights:
     def get(self, W):
         if not W.is_cuda:
             return None
-        if self.ref is W and self.version == W._version and self.addr == W.data_ptr() and self.buf is not None:
+        if (self.ref is W and self.version == W._version and self.addr == W.data_ptr()
+                and self.epoch == _PACK_EPOCH[0] and self.buf is not None):
             return self.buf
         K, c_in, c_out = (1,) + tuple(W.shape) if W.dim() == 2 else tuple(W.shape)
         if conv_packed_floats(K, c_in, c_out) == 0 or not W.is_contiguous():
@@ -282,7 +302,7 @@ class PackedWeights:
         with torch.no_grad():
             reuse = self.buf if (self.buf is not None and self.buf.device == W.device) else None
             self.buf = conv_pack(W.detach(), reuse)
-        self.ref, self.version, self.addr = W, W._version, W.data_ptr()
+        self.ref, self.version, self.addr, self.epoch = W, W._version, W.data_ptr(), _PACK_EPOCH[0]
         return self.buf
 
 

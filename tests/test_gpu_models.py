@@ -284,3 +284,31 @@ def test_fused_bn_relu_updown_conv_equals_module_by_module(batch, monkeypatch):
     for k in sa:
         if not k.endswith("kernel"):
             assert torch.equal(sa[k], sb[k]), k
+
+
+def test_packed_weight_cache_follows_fused_optimizer_steps(batch):
+    """The tensor-core operand images of a convolution kernel are cached per parameter (ops.PackedWeights).  The fused
+    Adam updates parameters without moving their version counters, so the cache must be invalidated by the optimizer
+    step itself: after every step the module must convolve with the NEW weights."""
+    from minsu3d_b200 import MinkowskiEngine as ME, ops
+    coords = batch["voxel_xyz"][:8000].contiguous()
+    x = torch.randn(coords.size(0), 16, device="cuda")
+    conv = ME.MinkowskiConvolution(16, 32, kernel_size=3, dimension=3).cuda()
+    for opt in (torch.optim.Adam(conv.parameters(), lr=0.05, fused=True), torch.optim.SGD(conv.parameters(), lr=0.5)):
+        for _ in range(2):
+            st = ME.SparseTensor(features=x, coordinates=coords)
+            y = conv(st).F
+            kmap = st.coordinate_manager.kernel_map(st.coordinate_map_key, st.coordinate_map_key, 3)
+            want = ops.conv_table(x, conv.kernel.detach(), kmap.nbr, kmap.n_out, 27, 16, 32, tile_mask=kmap.tile_mask)
+            assert torch.equal(y.detach(), want)  # packed image == image packed from the current weights
+            y.square().mean().backward()
+            before = conv.kernel.detach().clone()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            assert not torch.equal(before, conv.kernel.detach())
+    with torch.no_grad():
+        conv.kernel.mul_(0.5)  # in-place edit: version counter
+    st = ME.SparseTensor(features=x, coordinates=coords)
+    kmap = st.coordinate_manager.kernel_map(st.coordinate_map_key, st.coordinate_map_key, 3)
+    assert torch.equal(conv(st).F.detach(), ops.conv_table(x, conv.kernel.detach(), kmap.nbr, kmap.n_out, 27, 16, 32,
+                                                           tile_mask=kmap.tile_mask))

@@ -22,20 +22,33 @@ def ref():
 
 @pytest.fixture(scope="module")
 def batch():
+    """Two 20k-point scenes whose colour is a function of the semantic class (+ noise): the reference's clustering
+    stage is driven by the NETWORK's predictions (pointgroup.py:28-47), and it produces proposals only if the network
+    has learnt the semantics -- which a short training run can do when the class is visible in the features."""
     from minsu3d_b200.harness import scenes
-    return scenes.make_batch([21, 22], "cuda", n_points=20_000)
+    rng = np.random.default_rng(5)
+    palette = rng.uniform(-1, 1, (scenes.NUM_CLASSES, 3)).astype(np.float32)
+    out = []
+    for seed in (21, 22):
+        sc = scenes.make_scene(seed, 20_000)
+        sc["rgb"] = (palette[sc["sem_labels"]] + rng.normal(0, 0.05, sc["rgb"].shape)).astype(np.float32)
+        out.append(sc)
+    return scenes.collate(out, "cuda")
 
 
-def _pretrain(name, batch, steps=60):
+def _pretrain(name, batch, steps=250):
     """Random-init weights predict noise -> no proposals (SURVEY 8 caveat).  A short run of the harness trainer
     on the fixed batch (semantic + offset losses only) gives weights whose predictions cluster."""
     from minsu3d_b200.harness import models, train
-    cfg = models.Config.for_model(name, proposal_source="network")
+    cfg = models.Config.for_model(name, proposal_source="network", lr=0.01)
     tr = train.Trainer(cfg, "cuda", seed=7)
     tr.model.clustering = False
     for _ in range(steps):
         tr.step(batch)
     tr.model.clustering = True
+    with torch.no_grad():
+        acc = float((tr.model.backbone_forward(batch)["semantic_scores"].argmax(1) == batch["sem_labels"]).float().mean())
+    assert acc > 0.85, "pretraining did not learn the semantics (accuracy %.2f): no proposals would be found" % acc
     return cfg, tr.model
 
 
