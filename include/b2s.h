@@ -123,6 +123,9 @@ size_t b2s_conv_ws_bytes(int32_t K, int32_t c_in, int32_t c_out); /* scratch: pa
  * behaviour: 170 extra launches per PointGroup step).                                                          */
 int64_t b2s_conv_packed_floats(int32_t K, int32_t c_in, int32_t c_out);
 int b2s_conv_pack(const float* W, float* Wp, int32_t K, int32_t c_in, int32_t c_out, b2s_stream_t stream);
+/* The same for many layers in ONE launch: desc [n_desc, 6] int64 in device memory, row = {W, Wp, K, c_in, c_out, start},
+ * start = running sum of K*c_in*c_out over the preceding rows, total = the sum over all rows.                   */
+int b2s_conv_pack_multi(const int64_t* desc, int32_t n_desc, int64_t total, b2s_stream_t stream);
 /* add_src (optional, [n_out, c_out]): residual added to the result (common.py:48), folded into the epilogue of the
  * tcgen05 kernel.                                                                                              */
 int b2s_conv_table(const float* A, const float* W, const float* Wp, const int32_t* nbr, const uint32_t* tile_mask,
@@ -372,6 +375,24 @@ int b2s_proposal_iou(const uint64_t* keys_sorted, int64_t S, const int32_t* rema
                      float* iou, b2s_stream_t stream);
 int b2s_nms(const float* iou, const int32_t* order, int32_t n, float threshold, int32_t* pick, int32_t* d_count,
             void* ws, size_t ws_bytes, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY.md 8(f) #3 -- the loader's train-split sample pipeline on the GPU (general_dataset.py:80-165,
+ * util/transform.py:65-98).  Random draws are inputs (host pointers m9 / jitter3 / offset3 / range3 are read at call
+ * time).  Elastic distortion and the crop test run in double precision like the reference's numpy / scipy code.
+ *   b2s_aug_affine   : out_xyz = xyz @ M (float32), out_rgb = rgb + jitter (rgb may be NULL)
+ *   b2s_elastic_blur : noise [3][b0][b1][b2] float32 blurred in place by six separable 3-tap box passes
+ *                      (scipy.ndimage.convolve mode="constant"), tmp = scratch of the same size
+ *   b2s_elastic_apply: x [n,3] double += mag * trilinear(noise, x) on the grid linspace(-(b-1) gran, (b-1) gran, b)
+ *   b2s_crop_test    : out = pc + offset; valid[i] = out in [0, range); d_count[0] = number of valid points
+ * ---------------------------------------------------------------------------------------------- */
+int b2s_aug_affine(const float* xyz, const float* rgb, int64_t n, const float* m9_host, const float* jitter3_host,
+                   float* out_xyz, float* out_rgb, b2s_stream_t stream);
+int b2s_elastic_blur(float* noise, float* tmp, int32_t b0, int32_t b1, int32_t b2, b2s_stream_t stream);
+int b2s_elastic_apply(double* x, const float* noise, int64_t n, int32_t b0, int32_t b1, int32_t b2, double gran,
+                      double mag, b2s_stream_t stream);
+int b2s_crop_test(const double* pc, int64_t n, const double* offset3_host, const double* range3_host, double* out,
+                  uint8_t* valid, int32_t* d_count, b2s_stream_t stream);
 
 #ifdef __cplusplus
 }

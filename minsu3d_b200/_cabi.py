@@ -33,6 +33,7 @@ _SIGNATURES = {
     "b2s_conv_ws_bytes": (c_size, [c_i32, c_i32, c_i32]),
     "b2s_conv_packed_floats": (c_i64, [c_i32, c_i32, c_i32]),
     "b2s_conv_pack": (c_i32, [_P, _P, c_i32, c_i32, c_i32, _P]),
+    "b2s_conv_pack_multi": (c_i32, [_P, c_i32, c_i64, _P]),
     "b2s_conv_table": (c_i32, [_P, _P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P, c_size,
                                _P]),
     "b2s_conv_table_rows": (c_i32, [_P, _P, _P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P,
@@ -83,6 +84,10 @@ _SIGNATURES = {
     "b2s_proposal_npoint": (c_i32, [_P, c_i64, c_i32, _P, _P]),
     "b2s_proposal_iou": (c_i32, [_P, c_i64, _P, c_i32, _P, _P, _P]),
     "b2s_nms": (c_i32, [_P, _P, c_i32, c_f32, _P, _P, _P, c_size, _P]),
+    "b2s_aug_affine": (c_i32, [_P, _P, c_i64, _P, _P, _P, _P, _P]),
+    "b2s_elastic_blur": (c_i32, [_P, _P, c_i32, c_i32, c_i32, _P]),
+    "b2s_elastic_apply": (c_i32, [_P, _P, c_i64, c_i32, c_i32, c_i32, ctypes.c_double, ctypes.c_double, _P]),
+    "b2s_crop_test": (c_i32, [_P, c_i64, _P, _P, _P, _P, _P, _P]),
     "b2s_get_iou": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, _P]),
     "b2s_get_mask_label": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_f32, _P, _P, _P]),
 }
@@ -117,13 +122,13 @@ class _Namespace:
 # kernels launched by one call of each entry point (CUB scan = 2, 64-bit radix sort ~ 10);
 # used for the `gpu_launches` figure of bench.py
 KERNELS_PER_CALL = {
-    "b2s_coord_unique": 6, "b2s_kernel_map": 1, "b2s_pairs_from_nbr": 4, "b2s_conv_pack": 1, "b2s_conv_table": 1, "b2s_conv_table_rows": 1, "b2s_tile_order": 7, "b2s_conv_pairs": 1,
+    "b2s_coord_unique": 6, "b2s_kernel_map": 1, "b2s_pairs_from_nbr": 4, "b2s_conv_pack": 1, "b2s_conv_pack_multi": 1, "b2s_conv_table": 1, "b2s_conv_table_rows": 1, "b2s_tile_order": 7, "b2s_conv_pairs": 1,
     "b2s_conv_wgrad": 1, "b2s_resblock_forward": 6, "b2s_resblock_backward": 8, "b2s_bnconv_forward": 3, "b2s_bnconv_backward": 4, "b2s_bn_backward_add": 2, "b2s_bn_stats": 1, "b2s_bn_forward": 2, "b2s_bn_apply": 1, "b2s_bn_backward": 2, "b2s_gather_rows": 1,
     "b2s_scatter_add_rows": 1, "b2s_ballquery_count": 16, "b2s_ballquery_fill": 2, "b2s_cluster_label": 5,
     "b2s_cluster_select": 7, "b2s_cluster_order": 4, "b2s_cluster_centers": 1, "b2s_ha_assign": 1,
     "b2s_ha_concat": 4, "b2s_sec_mean": 1, "b2s_sec_min": 1, "b2s_sec_max": 1, "b2s_roipool_fp": 1,
     "b2s_roipool_bp": 1, "b2s_global_avg_pool_fp": 1, "b2s_global_avg_pool_bp": 1, "b2s_get_iou": 1, "b2s_clusters_voxelize": 2,
-    "b2s_get_mask_label": 1, "b2s_proposal_sort": 10, "b2s_proposal_npoint": 1, "b2s_proposal_iou": 2, "b2s_nms": 1,
+    "b2s_get_mask_label": 1, "b2s_aug_affine": 1, "b2s_elastic_blur": 6, "b2s_elastic_apply": 1, "b2s_crop_test": 1, "b2s_proposal_sort": 10, "b2s_proposal_npoint": 1, "b2s_proposal_iou": 2, "b2s_nms": 1,
 }
 _launches = [0]
 

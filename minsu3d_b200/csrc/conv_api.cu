@@ -11,6 +11,7 @@ int conv_wgrad_simt(const float*, const float*, const int32_t*, const int32_t*, 
 bool conv_tc_supported(int K, int c_in, int c_out);
 size_t conv_tc_ws_bytes(int K, int c_in, int c_out);
 int conv_tc_pack_both(const float* W, float* Bp, int K, int c_in, int c_out, cudaStream_t stream);
+int conv_tc_pack_multi(const int64_t* desc, int n_desc, int64_t total, cudaStream_t stream);
 const float* conv_tc_weights(const float* W, const float* Wp, int K, int c_in, int c_out, int wT, void* ws,
                              cudaStream_t stream);
 int conv_tc(const float* A, const float* W, const float* Wp, const int32_t* idx, const int32_t* dst, const int32_t* k_offsets,
@@ -103,6 +104,14 @@ int b2s_conv_pack(const float* W, float* Wp, int32_t K, int32_t c_in, int32_t c_
     return B2S_E_INVALID;
   }
   return conv_tc_pack_both(W, Wp, K, c_in, c_out, stream);
+}
+
+int b2s_conv_pack_multi(const int64_t* desc, int32_t n_desc, int64_t total, b2s_stream_t stream) {
+  if (!desc || n_desc < 0 || total < 0) {
+    set_error("conv_pack_multi: invalid argument");
+    return B2S_E_INVALID;
+  }
+  return conv_tc_pack_multi(desc, n_desc, total, stream);
 }
 
 int b2s_conv_table(const float* A, const float* W, const float* Wp, const int32_t* nbr, const uint32_t* tile_mask,

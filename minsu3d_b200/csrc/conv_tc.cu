@@ -525,6 +525,53 @@ int conv_tc_pack_both(const float* W, float* Bp, int K, int c_in, int c_out, cud
   return check_launch("conv_pack");
 }
 
+// Every convolution kernel of a model in ONE launch (the trainer calls this right after optimizer.step()).
+// desc[i] = {W pointer, Wp pointer, K, c_in, c_out, first element index} as six int64; element = one (k, c_in, c_out)
+// entry of a layer; each thread writes the four images of its element (forward hi/lo, transposed hi/lo).
+__global__ void __launch_bounds__(256)
+    pack_weights_multi_kernel(const int64_t* __restrict__ desc, int n_desc, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  int lo = 0, hi = n_desc - 1;  // last descriptor whose start <= e
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(desc + mid * 6 + 5) <= e) lo = mid;
+    else hi = mid - 1;
+  }
+  const int64_t* d = desc + lo * 6;
+  const float* W = (const float*)__ldg(d + 0);
+  float* Bp = (float*)__ldg(d + 1);
+  const int c_in = (int)__ldg(d + 3), c_out = (int)__ldg(d + 4);
+  const int64_t half = __ldg(d + 2) * c_in * c_out;
+  const int64_t i = e - __ldg(d + 5);  // flat index into W[k][ci][co]
+  const int co = (int)(i % c_out);
+  const int ci = (int)((i / c_out) % c_in);
+  const int64_t k = i / ((int64_t)c_out * c_in);
+  const float v = W[i];
+  const float vh = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  const float vl = v - vh;
+  // forward image: product c_in -> c_out, slab (k, ci / 16), row n = co, column j = ci % 16
+  {
+    const int64_t slab = k * (c_in >> 4) + (ci >> 4);
+    const int64_t off = slab * (c_out * 16) + (sw64_offset(co, ci & 15) >> 2);
+    Bp[off] = vh;
+    Bp[half + off] = vl;
+  }
+  // transposed image: product c_out -> c_in, slab (k, co / 16), row n = ci, column j = co % 16
+  {
+    const int64_t slab = k * (c_out >> 4) + (co >> 4);
+    const int64_t off = slab * (c_in * 16) + (sw64_offset(ci, co & 15) >> 2);
+    Bp[2 * half + off] = vh;
+    Bp[3 * half + off] = vl;
+  }
+}
+
+int conv_tc_pack_multi(const int64_t* desc, int n_desc, int64_t total, cudaStream_t stream) {
+  if (n_desc <= 0 || total <= 0) return B2S_OK;
+  pack_weights_multi_kernel<<<(unsigned)cdiv(total, 256), 256, 0, stream>>>(desc, n_desc, total);
+  return check_launch("conv_pack_multi");
+}
+
 // the image pair one product needs: packed by the caller (Wp, both orientations) or packed here into ws
 const float* conv_tc_weights(const float* W, const float* Wp, int K, int c_in, int c_out, int wT, void* ws,
                              cudaStream_t stream) {

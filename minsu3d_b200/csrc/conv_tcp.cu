@@ -18,8 +18,8 @@
 //   * Gather staging.  Default: three register slots per producer thread (two slabs of LDG.256 in flight), the next
 //     item's first loads issued before the accumulator is drained.  The round-2 ncu capture of this kernel on the
 //     level-0 map (profiles/r02_conv_tcp_ncu.txt) shows a latency-bound gather -- 41 % of the warp samples wait on the
-//     first use of a gathered register, 0.43 eligible warps per scheduler, issue slots 32 %, L2 at 44 % of its
-//     throughput cap -- and two remedies were built and MEASURED SLOWER, so they are not the default:
+//     first use of a gathered register, 0.43 eligible warps per scheduler, issue slots 32 %, L2 throughput 33 % of its
+//     peak -- and two remedies were built and MEASURED SLOWER, so they are not the default:
 //       - ASYNC (B2S_TC_ASYNC=1, kept as an experiment switch): every producer thread copies its neighbour rows with
 //         cp.async.cg into a thread-private, XOR-swizzled row of a 5-deep shared-memory ring (five slabs in flight, no
 //         registers, cursor runs ahead across item boundaries) and reads it back with conflict-free LDS.128.  cp.async

@@ -175,7 +175,7 @@ class Config:
     def for_model(name, **kw):
         base = dict(model=name)
         if name == "hais":
-            base.update(m=32, score_fullscale=20, lr=0.0015)
+            base.update(m=32, score_fullscale=20, lr=0.0015, fg_thresh=1.0, bg_thresh=0.0)  # hais.yaml:31-35
         elif name == "softgroup":
             base.update(m=32, score_fullscale=20, lr=0.004)
         base.update(kw)

@@ -51,6 +51,13 @@ class Trainer:
         # host cost of the ~200-parameter step at a few launches (the default foreach path costs ~5 ms of Python)
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr, fused=(self.device.type == "cuda"))
         self.last_losses = None
+        # tensor-core operand images of every convolution kernel: refreshed in one launch after each optimizer step
+        # (the modules would otherwise re-pack lazily, one launch per layer per step)
+        self.packed = None
+        if self.device.type == "cuda":
+            from ..MinkowskiEngine.modules import _ConvBase
+            self.packed = ops.PackedSet([(m.kernel, m._packed) for m in self.model.modules() if isinstance(m, _ConvBase)])
+            self.packed.repack()
 
     def step(self, data):
         """data already on the device.  Returns the total loss (device scalar)."""
@@ -64,6 +71,8 @@ class Trainer:
         if self.device.type == "cuda":
             self.optimizer.found_inf = ops.deferred_failure_flag(self.device)
         self.optimizer.step()
+        if self.packed is not None:
+            self.packed.repack()
         self.last_losses = losses
         return total.detach()
 

@@ -306,6 +306,45 @@ class PackedWeights:
         return self.buf
 
 
+class PackedSet:
+    """All tensor-core-eligible convolution kernels of a model, re-packed in ONE launch (b2s_conv_pack_multi).
+
+    `caches`: list of (parameter, PackedWeights) -- e.g. (conv.kernel, conv._packed) of every MinkowskiConvolution.
+    repack() refreshes every image and stamps the per-parameter caches as current, so the modules' lazy
+    `PackedWeights.get()` finds them valid: call it right after optimizer.step()."""
+
+    def __init__(self, caches):
+        self.items = []
+        rows, start = [], 0
+        for W, cache in caches:
+            if not (W.is_cuda and W.is_contiguous() and W.dtype == torch.float32):
+                continue
+            K, c_in, c_out = (1,) + tuple(W.shape) if W.dim() == 2 else tuple(W.shape)
+            n = conv_packed_floats(K, c_in, c_out)
+            if n == 0:
+                continue
+            buf = torch.empty(n, dtype=torch.float32, device=W.device)
+            rows.append([W.data_ptr(), buf.data_ptr(), K, c_in, c_out, start])
+            start += K * c_in * c_out
+            self.items.append((W, cache, buf))
+        self.total = start
+        self.desc = (torch.tensor(rows, dtype=torch.int64, device=self.items[0][0].device) if rows else None)
+
+    def repack(self):
+        if self.desc is None:
+            return
+        for W, _, buf in self.items:  # the table holds raw addresses: parameters must not have been moved
+            require(W.data_ptr() == int(self._addr(W)), "PackedSet: a parameter was moved; rebuild the set")
+        check(lib().b2s_conv_pack_multi(ptr(self.desc), len(self.items), self.total, stream()), "conv_pack_multi")
+        for W, cache, buf in self.items:
+            cache.ref, cache.version, cache.addr, cache.epoch, cache.buf = W, W._version, W.data_ptr(), _PACK_EPOCH[0], buf
+
+    def _addr(self, W):
+        if not hasattr(self, "_addr_of"):
+            self._addr_of = {id(w): w.data_ptr() for w, _, _ in self.items}
+        return self._addr_of[id(W)]
+
+
 def conv_table(A, W, nbr, n_out, K, c_in, c_out, w_transposed=False, k_reversed=False, algo=None, tile_mask=None,
                out_rows=None, packed=None, add_src=None):
     """out_rows: nbr / tile_mask are the mask-sorted table of tile_order() and out_rows its row permutation.

@@ -504,3 +504,45 @@ def test_postproc_restatement_edge_cases():
     assert empty["label_id"].size == 0 and empty["mask_offsets"].tolist() == [0] and empty["bbox"].shape == (0, 6)
     hs = postproc.hais_pred_instances(xyz, scores, pidx, 3, np.ones((pidx.shape[0], 1), np.float32), sem, 2, -0.5, 0.09, 15)
     assert hs["proposal"].tolist() == [0, 1, 2]  # no NMS in HAIS, >= on the point count
+
+
+# ------------------------------------------------------------------------------------------------
+# the numpy restatement of the loader's sample pipeline pinned by the reference's own transform code
+# ------------------------------------------------------------------------------------------------
+def test_dataset_restatement_matches_reference_transform_functions():
+    """oracle/dataset_ref.py calls np.random in the reference's order: seeded equally, the reference's own jitter /
+    flip / rotz / elastic (minsu3d/util/transform.py, imported from /root/reference or the staged copy) give
+    bit-identical results."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from ref_loader import load_reference_models
+    if load_reference_models() is None:
+        pytest.skip("reference python not available")
+    from minsu3d.util import transform as T
+    from minsu3d_b200.harness import scenes
+    from oracle import dataset_ref
+    sc = scenes.make_scene(3, 20000)
+    np.random.seed(11)
+    data, draws = dataset_ref.train_sample(sc)
+    np.random.seed(11)
+    m = np.eye(3)
+    m = np.matmul(m, T.jitter())
+    m *= T.flip(0, random=True)
+    m = np.matmul(m, T.rotz(np.random.rand() * 2 * np.pi)).astype(np.float32)
+    xyz = np.matmul(sc["xyz"].astype(np.float32), m)
+    rgb_jit = np.random.randn(3) * 0.1
+    scale = 1 / 0.02
+    e = T.elastic(xyz * scale, 6 * scale // 50, 40 * scale / 50)
+    e = T.elastic(e, 20 * scale // 50, 160 * scale / 50)
+    e -= e.min(axis=0)
+    e /= scale
+    assert np.array_equal(m, draws["aug_matrix"]) and np.array_equal(rgb_jit, draws["rgb_jitter"])
+    assert np.array_equal(xyz, data["point_xyz"])
+    assert np.array_equal(e, data["point_xyz_elastic"])
+    # crop with a small budget: same valid set as the reference's crop on the same draws
+    np.random.seed(3)
+    pc = e * scale
+    a, va = dataset_ref.crop(pc, 8000, 512, [])
+    np.random.seed(3)
+    b, vb = T.crop(pc, 8000, 512)
+    assert np.array_equal(va, vb) and np.array_equal(a, b) and va.sum() <= 8000
