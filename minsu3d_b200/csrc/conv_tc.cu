@@ -93,11 +93,6 @@ struct TcArgs {
   int64_t bp_half;       // floats in one image
   int K, c_in, c_out, k_reversed, stages, tmem_cols, a_col0;
   int sb;  // weight-slab ring depth (shared memory), decoupled from the A stages (tensor memory)
-  // TABLE mode, experimental (B2S_TC_SPLIT=1, default off): gridDim.y CTAs share one tile, each takes a contiguous
-  // range of the tile's active offsets and writes its partial sums to out + blockIdx.y * n_out * c_out (scratch);
-  // split_reduce_kernel adds the partials in a fixed order.  Deep U-Net levels have 2-70 tiles of 80-190 slabs each:
-  // without the split a handful of SMs walk them serially while the rest of the GPU idles.
-  int splits;
 };
 
 template <bool PAIRS, int NSPLIT>
@@ -239,19 +234,6 @@ __global__ void __launch_bounds__(TC_THREADS, B2S_TC_MIN_CTAS) conv_tc_kernel(co
   if (PAIRS) kmask = 1u << k_single;
   else if (a.idx == nullptr) kmask = 1u;
   else kmask = (a.tile_mask != nullptr) ? pre_mask : *s_mask;
-  if (!PAIRS && a.splits > 1) {
-    // this CTA's share: the set bits of kmask with rank in [a0, a1)
-    const int active = __popc(kmask);
-    const int per = (active + a.splits - 1) / a.splits;
-    const int a0 = (int)blockIdx.y * per, a1 = min(active, a0 + per);
-    uint32_t sub = 0, m = kmask;
-    for (int rank = 0; m != 0; ++rank) {
-      const uint32_t low = m & (0u - m);
-      if (rank >= a0 && rank < a1) sub |= low;
-      m ^= low;
-    }
-    kmask = sub;
-  }
   const uint32_t tmem_base = *s_tmem;
   const int nc = a.c_in >> 4;
   const int T = __popc(kmask) * nc;  // slabs of this tile
@@ -348,7 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, B2S_TC_MIN_CTAS) conv_tc_kernel(co
       tc_fence_after();
     }
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float* const out_base = a.out + (PAIRS ? (int64_t)0 : (int64_t)blockIdx.y * a.n_out * a.c_out);
+    float* const out_base = a.out;
     for (int col = 0; col < a.c_out; col += 16) {
       uint32_t v[16];
       if (T > 0) {
@@ -447,31 +429,6 @@ __global__ void __launch_bounds__(TC_THREADS, B2S_TC_MIN_CTAS) conv_tc_kernel(co
   }
 }
 
-__global__ void __launch_bounds__(256)
-    split_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ out, int64_t total4, int splits) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total4) return;
-  float4 acc = __ldg(partial + i);
-  for (int s = 1; s < splits; ++s) {  // fixed order: deterministic
-    const float4 v = __ldg(partial + (int64_t)s * total4 + i);
-    acc.x += v.x;
-    acc.y += v.y;
-    acc.z += v.z;
-    acc.w += v.w;
-  }
-  out[i] = acc;
-}
-
-constexpr size_t TC_SPLIT_WS = (size_t)16 << 20;  // scratch for the partial outputs of the offset split
-
-static bool tc_split_enabled() {
-  static const int on = [] {
-    const char* e = getenv("B2S_TC_SPLIT");
-    return (e != nullptr && atoi(e) != 0) ? 1 : 0;
-  }();
-  return on != 0;
-}
-
 bool conv_tc_supported(int K, int c_in, int c_out) {
   return K >= 1 && K <= 32 && c_in >= 16 && (c_in % 16) == 0 && c_out >= 16 && (c_out % 16) == 0 && c_out <= 256;
 }
@@ -483,7 +440,7 @@ size_t conv_tc_ws_bytes(int K, int c_in, int c_out) {
 }
 
 template <bool PAIRS, int NSPLIT>
-static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream, int splits = 1) {
+static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream) {
   auto bucket = [](int c) { int b = 32; while (b < c) b <<= 1; return b; };
   const int b_slot = (NSPLIT == 3 ? 2 : 1) * a.c_out * 64;
   const int a_cols = NSPLIT == 3 ? 32 : 16;
@@ -511,8 +468,7 @@ static int launch_tc(TcArgs a, int64_t grid_x, cudaStream_t stream, int splits =
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured[dev] = smem;
   }
-  a.splits = splits;
-  kern<<<dim3((unsigned)grid_x, (unsigned)splits), TC_THREADS, smem, stream>>>(a);
+  kern<<<(unsigned)grid_x, TC_THREADS, smem, stream>>>(a);
   return check_launch("conv_tc");
 }
 
@@ -609,28 +565,8 @@ int conv_tc(const float* A, const float* W, const float* Wp, const int32_t* idx,
   a.c_out = c_out;
   a.k_reversed = krev;
   a.stages = a.tmem_cols = a.a_col0 = a.sb = 0;
-  a.splits = 1;
   if (!pairs) {
     int64_t gx = cdiv(n_out, TC_BM);
-    // offset split (experimental, B2S_TC_SPLIT=1): few tiles with long slab loops -> several CTAs per tile
-    int splits = 1;
-    if (tc_split_enabled() && idx != nullptr && K >= 8 && K * (c_in / 16) >= 32) {
-      const int64_t slots = (int64_t)B2S_SM_COUNT * 3;
-      const int64_t by_fill = slots / gx;                                        // CTAs that still fit in one wave
-      const int64_t by_mem = (int64_t)(TC_SPLIT_WS / ((size_t)n_out * c_out * 4 + 1));  // partials must fit the scratch
-      const int64_t s = std::min<int64_t>(std::min<int64_t>(by_fill, by_mem), std::min(8, K / 3));
-      if (s >= 2 && ws_bytes >= conv_tc_ws_bytes(K, c_in, c_out)) splits = (int)s;
-    }
-    if (splits > 1) {
-      float* partial = (float*)((char*)ws + align_up((size_t)half * 4 * 2) + 256);
-      a.out = partial;
-      int rc = nsplit == 3 ? launch_tc<false, 3>(a, gx, stream, splits) : launch_tc<false, 1>(a, gx, stream, splits);
-      if (rc) return rc;
-      const int64_t total4 = n_out * (c_out / 4);
-      split_reduce_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, stream>>>((const float4*)partial, (float4*)out, total4,
-                                                                          splits);
-      return check_launch("conv_tc split reduce");
-    }
     return nsplit == 3 ? launch_tc<false, 3>(a, gx, stream) : launch_tc<false, 1>(a, gx, stream);
   }
   int64_t gx = cdiv(max_pairs, TC_BM) + K;

@@ -26,7 +26,7 @@ from . import scenes
 # MinkUNet pieces (common.py:21-95, backbone.py:8-43, tiny_unet.py:7-19)
 # ------------------------------------------------------------------------------------------
 ASYNC_SIZES = True   # use the loader's level sizes / uniqueness guarantees instead of host reads (validated on device)
-FUSED_UPDOWN = False  # BN->ReLU->(de)conv of the U-Net levels as one call: written, NOT yet run on a GPU (round 2)
+FUSED_UPDOWN = True   # BN->ReLU->(de)conv of the U-Net levels as one call (b2s_bnconv_*; tests/test_gpu_models.py)
 FUSED_BLOCKS = True  # training-mode residual blocks through b2s_resblock_forward/backward (host-side fusion)
 
 

@@ -2,9 +2,11 @@
 against the numpy restatement oracle/dataset_ref.py (itself pinned bit-exact against the reference's own
 transform.elastic / jitter / flip / rotz in tests/test_cpu_oracle_and_host.py) ON SHARED RANDOM DRAWS.
 
-Tolerances: augmented coordinates 1e-6 (float32 dot product order), elastic coordinates 1e-9 relative (double
-precision on both sides, same evaluation order), voxel coordinates: identical for all but at most 1e-4 of the points
-(a point within 1e-9 of a voxel face may round differently), maps consistent with the coordinates."""
+Tolerances: augmented coordinates 1e-6 (float32 dot product: numpy's sgemm uses FMA in an unspecified order, the
+kernel separate multiplies and adds -- one float32 ulp).  That ulp is the input of everything downstream, so the
+elastic coordinates (double precision on both sides; the elastic kernels alone match scipy to 1e-9, second test) agree
+to 2e-6 m, and the voxel coordinates are identical for all but at most 5e-4 of the points (a point within ~1e-6 m of
+a voxel face rounds to the other side); where they are identical the maps and features must be identical too."""
 import numpy as np
 import pytest
 import torch
@@ -37,7 +39,7 @@ def test_gpu_train_sample_matches_numpy_restatement_on_shared_draws(n, max_pts):
     assert got["point_xyz"].shape == want["point_xyz"].shape
     assert np.abs(got["point_xyz"].cpu().numpy() - want["point_xyz"]).max() < 1e-6
     e_got, e_want = got["point_xyz_elastic"].cpu().numpy(), want["point_xyz_elastic"]
-    assert np.abs(e_got - e_want).max() <= 1e-9 * max(1.0, np.abs(e_want).max())
+    assert np.abs(e_got - e_want).max() <= 2e-6
     assert np.array_equal(got["sem_labels"].cpu().numpy(), want["sem_labels"])
     assert np.array_equal(got["instance_ids"].cpu().numpy(), want["instance_ids"])
     assert int(got["num_instance"]) == int(want["num_instance"])
@@ -49,8 +51,16 @@ def test_gpu_train_sample_matches_numpy_restatement_on_shared_draws(n, max_pts):
     vx_g = got["voxel_xyz"].cpu().numpy()[got["voxel_point_map"].cpu().numpy()]
     vx_w = want["voxel_xyz"][want["voxel_point_map"]]
     differ = (vx_g != vx_w).any(1).mean()
-    assert differ <= 1e-4, differ
-    if differ == 0:  # identical quantisation -> identical first-occurrence order, maps and features
+    assert differ <= 5e-4, differ
+    # the voxel set and the first-occurrence structure are self-consistent: every voxel's features are those of its
+    # first point, every point maps to the voxel with its own quantised coordinate
+    vmap = got["voxel_point_map"]
+    q = torch.floor(got["point_xyz_elastic"] / 0.02).to(torch.int32)
+    assert torch.equal(got["voxel_xyz"][vmap], q)
+    first = torch.full((got["voxel_xyz"].size(0),), vmap.numel(), dtype=torch.int64, device="cuda").scatter_reduce_(
+        0, vmap, torch.arange(vmap.numel(), device="cuda"), reduce="amin")
+    assert torch.equal(first, torch.sort(first).values)  # first-occurrence order
+    if differ == 0:  # identical quantisation -> identical voxel list, maps and features
         assert np.array_equal(got["voxel_xyz"].cpu().numpy(), want["voxel_xyz"])
         assert np.array_equal(got["voxel_point_map"].cpu().numpy(), want["voxel_point_map"])
         assert np.abs(got["voxel_features"].cpu().numpy() - want["voxel_features"]).max() < 1e-6
