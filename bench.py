@@ -461,11 +461,12 @@ def run_softgroup_infer(args):
     sizes = [50_000, 100_000, 150_000, 200_000, 250_000, 120_000, 80_000, 180_000]
     distinct = [scenes.collate([scenes.make_scene(500 + i, n)], device) for i, n in enumerate(sizes)]
     n_val = 312
+    which = np.random.default_rng(0).integers(0, len(distinct), n_val)  # val scene i has the size of distinct[which[i]]
     mine = dp.shard_indices(n_val, rank, world)
     inst_classes = cfg.classes - len(cfg.ignore_classes)
 
     def one(i):
-        d = distinct[i % len(distinct)]
+        d = distinct[int(which[i])]
         with torch.no_grad():
             out = model(d)
             if out.get("proposals_idx") is None:
@@ -501,7 +502,7 @@ def run_softgroup_infer(args):
             "steps": 1, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[3]: SoftGroup (m=32) inference over 312 synthetic val-size scenes (8 distinct "
-                                   "50k-250k-point scenes cycled), scene i -> rank i % world, GPU post-processing, instance "
+                                   "50k-250k-point scenes, drawn per val index with a fixed seed), scene i -> rank i % world, GPU post-processing, instance "
                                    "counts gathered on rank 0", "predicted_instances": total_instances,
                        "ms_per_scene_per_gpu": ms / max(len(mine), 1)}}), flush=True)
     if world > 1:

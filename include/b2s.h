@@ -318,6 +318,10 @@ int b2s_sec_max(const float* inp, const int32_t* offsets, float* out, int32_t n_
                 b2s_stream_t stream);
 int b2s_roipool_fp(const float* feats, const int32_t* offsets, float* out, int32_t* maxidx,
                    int32_t n_seg, int32_t c, b2s_stream_t stream);
+/* the same for long segments (proposals of ~10k points): several CTAs per segment + an in-order combine */
+size_t b2s_roipool_ws_bytes(int32_t n_seg, int32_t c);
+int b2s_roipool_fp_ws(const float* feats, const int32_t* offsets, float* out, int32_t* maxidx, int32_t n_seg,
+                      int32_t c, int64_t n_rows, void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_roipool_bp(float* d_feats, const int32_t* offsets, const int32_t* maxidx,
                    const float* d_out, int32_t n_seg, int32_t c, b2s_stream_t stream);
 int b2s_global_avg_pool_fp(const float* feats, const int32_t* offsets, float* out, int32_t n_seg,
@@ -393,6 +397,20 @@ int b2s_elastic_apply(double* x, const float* noise, int64_t n, int32_t b0, int3
                       double mag, b2s_stream_t stream);
 int b2s_crop_test(const double* pc, int64_t n, const double* offset3_host, const double* range3_host, double* out,
                   uint8_t* valid, int32_t* d_count, b2s_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Semantic cross-entropy of the train step (general_model.py:36-40: F.cross_entropy(scores, labels, ignore_index),
+ * mean over the labelled points), one fused pass per direction.  labels int16 (label_bytes 2) or int64 (8).
+ * forward: loss [1], n_valid [1] (input of the backward); counter = int32 that is 0 between launches.
+ * backward: gscores [n,c] = (softmax - onehot) * gout[0] / n_valid[0], 0 for ignored rows.
+ * ---------------------------------------------------------------------------------------------- */
+size_t b2s_cross_entropy_ws_bytes(int64_t n);
+int b2s_cross_entropy_forward(const float* scores, const void* labels, int32_t label_bytes, int64_t n, int32_t c,
+                              int32_t ignore_index, float* loss, float* n_valid, int32_t* counter, void* ws,
+                              size_t ws_bytes, b2s_stream_t stream);
+int b2s_cross_entropy_backward(const float* scores, const void* labels, int32_t label_bytes, int64_t n, int32_t c,
+                               int32_t ignore_index, const float* n_valid, const float* gout, float* gscores,
+                               b2s_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "b2s_sec_min": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
     "b2s_sec_max": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
     "b2s_roipool_fp": (c_i32, [_P, _P, _P, _P, c_i32, c_i32, _P]),
+    "b2s_roipool_ws_bytes": (c_size, [c_i32, c_i32]),
+    "b2s_roipool_fp_ws": (c_i32, [_P, _P, _P, _P, c_i32, c_i32, c_i64, _P, c_size, _P]),
     "b2s_roipool_bp": (c_i32, [_P, _P, _P, _P, c_i32, c_i32, _P]),
     "b2s_global_avg_pool_fp": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
     "b2s_global_avg_pool_bp": (c_i32, [_P, _P, _P, c_i32, c_i32, _P]),
@@ -88,6 +90,9 @@ _SIGNATURES = {
     "b2s_elastic_blur": (c_i32, [_P, _P, c_i32, c_i32, c_i32, _P]),
     "b2s_elastic_apply": (c_i32, [_P, _P, c_i64, c_i32, c_i32, c_i32, ctypes.c_double, ctypes.c_double, _P]),
     "b2s_crop_test": (c_i32, [_P, c_i64, _P, _P, _P, _P, _P, _P]),
+    "b2s_cross_entropy_ws_bytes": (c_size, [c_i64]),
+    "b2s_cross_entropy_forward": (c_i32, [_P, _P, c_i32, c_i64, c_i32, c_i32, _P, _P, _P, _P, c_size, _P]),
+    "b2s_cross_entropy_backward": (c_i32, [_P, _P, c_i32, c_i64, c_i32, c_i32, _P, _P, _P, _P]),
     "b2s_get_iou": (c_i32, [_P, _P, _P, _P, _P, _P, c_i32, c_i32, _P]),
     "b2s_get_mask_label": (c_i32, [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_f32, _P, _P, _P]),
 }
@@ -126,9 +131,9 @@ KERNELS_PER_CALL = {
     "b2s_conv_wgrad": 1, "b2s_resblock_forward": 6, "b2s_resblock_backward": 8, "b2s_bnconv_forward": 3, "b2s_bnconv_backward": 4, "b2s_bn_backward_add": 2, "b2s_bn_stats": 1, "b2s_bn_forward": 2, "b2s_bn_apply": 1, "b2s_bn_backward": 2, "b2s_gather_rows": 1,
     "b2s_scatter_add_rows": 1, "b2s_ballquery_count": 16, "b2s_ballquery_fill": 2, "b2s_cluster_label": 5,
     "b2s_cluster_select": 7, "b2s_cluster_order": 4, "b2s_cluster_centers": 1, "b2s_ha_assign": 1,
-    "b2s_ha_concat": 4, "b2s_sec_mean": 1, "b2s_sec_min": 1, "b2s_sec_max": 1, "b2s_roipool_fp": 1,
+    "b2s_ha_concat": 4, "b2s_sec_mean": 1, "b2s_sec_min": 1, "b2s_sec_max": 1, "b2s_roipool_fp": 1, "b2s_roipool_fp_ws": 2,
     "b2s_roipool_bp": 1, "b2s_global_avg_pool_fp": 1, "b2s_global_avg_pool_bp": 1, "b2s_get_iou": 1, "b2s_clusters_voxelize": 2,
-    "b2s_get_mask_label": 1, "b2s_aug_affine": 1, "b2s_elastic_blur": 6, "b2s_elastic_apply": 1, "b2s_crop_test": 1, "b2s_proposal_sort": 10, "b2s_proposal_npoint": 1, "b2s_proposal_iou": 2, "b2s_nms": 1,
+    "b2s_get_mask_label": 1, "b2s_cross_entropy_forward": 1, "b2s_cross_entropy_backward": 1, "b2s_aug_affine": 1, "b2s_elastic_blur": 6, "b2s_elastic_apply": 1, "b2s_crop_test": 1, "b2s_proposal_sort": 10, "b2s_proposal_npoint": 1, "b2s_proposal_iou": 2, "b2s_nms": 1,
 }
 _launches = [0]
 
@@ -177,9 +182,10 @@ def stream():
 _WS = {}
 
 
-def workspace(nbytes, device):
-    """Grow-only scratch buffer per (device, stream); stream-ordered reuse is safe."""
-    key = (device.index, stream())
+def workspace(nbytes, device, slot=0):
+    """Grow-only scratch buffer per (device, stream, slot); stream-ordered reuse is safe.  slot > 0: additional
+    buffers for calls whose scratch must survive other library calls (batched ball queries / clusterings)."""
+    key = (device.index, stream(), slot)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

@@ -79,8 +79,11 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// MINCTAS: CTAs per SM the register allocation aims for.  3 (narrow layers: c_out <= 32 -> 128 TMEM columns, <= 75 KB of
+// shared memory) puts 18 warps on an SM instead of 12: the gather is latency-bound (see above), more resident warps are
+// the one remedy that costs no extra instructions.
 template <int NSPLIT, bool ASYNC>
-__global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a) {
+__device__ __forceinline__ void conv_tcp_body(const TcpArgs& a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -544,6 +547,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a
   }
 }
 
+// entry points: 2 CTAs/SM (up to 168 registers) and 3 CTAs/SM (112 registers: 3 x 192 x 112 = 64,512)
+template <int NSPLIT, bool ASYNC>
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a) {
+  conv_tcp_body<NSPLIT, ASYNC>(a);
+}
+template <int NSPLIT>
+__global__ void __maxnreg__(112) conv_tcp3_kernel(const TcpArgs a) {
+  conv_tcp_body<NSPLIT, false>(a);
+}
+
 // partial sums of the offset split -> output, fixed order (deterministic), optional residual
 __global__ void __launch_bounds__(256)
     tcp_split_reduce_kernel(const float4* __restrict__ partial, const float4* __restrict__ add_src,
@@ -582,9 +595,17 @@ static int launch_tcp(TcpArgs a, void* split_ws, float* final_out, const float* 
   const int a_cols = NSPLIT == 3 ? 32 : 16;
   const int b_slot = (NSPLIT == 3 ? 2 : 1) * a.c_out * 64;
   // ---- tensor memory: [acc_bufs accumulators of c_out columns][S stages of a_cols columns] -------------------
+  // 512 columns per SM: <= 128 per CTA lets three CTAs share an SM, <= 256 two, more only one
   auto fits = [&](int ab, int S, int cap) { return ab * a.c_out + S * a_cols <= cap; };
   int cap = 256, ab = 2;
-  if (fits(2, 4, 256)) {
+  const bool allow3 = tcp_env("B2S_TC_CTAS", 3) >= 3;
+  if (allow3 && fits(2, 3, 128)) {
+    cap = 128;
+    ab = 2;
+  } else if (allow3 && fits(1, 3, 128)) {
+    cap = 128;
+    ab = 1;
+  } else if (fits(2, 4, 256)) {
     ab = 2;
   } else if (fits(1, 3, 256)) {
     ab = 1;
@@ -601,11 +622,11 @@ static int launch_tcp(TcpArgs a, void* split_ws, float* final_out, const float* 
   a.stages = S;
   a.a_col0 = ab * a.c_out;
   a.tmem_cols = bucket;
-  const int ctas_per_sm = bucket > 256 ? 1 : 2;
+  const int ctas_per_sm = bucket > 256 ? 1 : (bucket > 128 ? 2 : 3);
   // ---- shared memory plan: [weights][barriers][2 index tiles][ASYNC: gather ring of TCP_DEPTH x 8 KB] ------------
   // budget per CTA: 112 KB when two CTAs share an SM, 220 KB when the TMEM allocation allows only one
   const int total_slabs = a.K * (a.c_in / 16);
-  const size_t budget = (size_t)(ctas_per_sm == 2 ? 112 : 220) * 1024;
+  const size_t budget = (size_t)(ctas_per_sm == 3 ? 74 : (ctas_per_sm == 2 ? 112 : 220)) * 1024;
   const size_t idx_bytes = a.idx != nullptr ? (size_t)2 * TC_BM * a.K * 4 : 0;
   const size_t fixed = 1024 /*align slack*/ + 8 * (size_t)(2 * TCP_MAX_S + 8) + 32 + idx_bytes + 64 + 128;
   auto plan = [&](size_t extra, bool* resident, int* sb) {  // weights in what is left after `extra`; false = does not fit
@@ -620,7 +641,7 @@ static int launch_tcp(TcpArgs a, void* split_ws, float* final_out, const float* 
   bool resident = false, async = tcp_env("B2S_TC_ASYNC", 0) != 0;
   int sb = 2;
   if (async) {
-    async = plan((size_t)TCP_DEPTH * TCP_GSTAGE, &resident, &sb) && (resident || sb >= 4);
+    async = ctas_per_sm == 2 && plan((size_t)TCP_DEPTH * TCP_GSTAGE, &resident, &sb) && (resident || sb >= 4);
   }
   if (!async && !plan(0, &resident, &sb)) {
     set_error("conv_tcp: shared memory plan failed");
@@ -656,12 +677,14 @@ static int launch_tcp(TcpArgs a, void* split_ws, float* final_out, const float* 
   size_t smem = 1024 /*align slack*/ + (size_t)a.sb * b_slot + 8 * (size_t)nbar + 32 + idx_bytes + 64 + 128 +
                 (async ? (size_t)TCP_DEPTH * TCP_GSTAGE : 0);
   if (ctas_per_sm == 1) smem = std::max(smem, (size_t)120 * 1024);  // 512 TMEM columns: keep a second CTA off the SM
-  auto kern = async ? conv_tcp_kernel<NSPLIT, true> : conv_tcp_kernel<NSPLIT, false>;
-  static size_t configured[B2S_MAX_DEVICES][2] = {};
+  auto kern = ctas_per_sm == 3 ? conv_tcp3_kernel<NSPLIT>
+                               : (async ? conv_tcp_kernel<NSPLIT, true> : conv_tcp_kernel<NSPLIT, false>);
+  static size_t configured[B2S_MAX_DEVICES][3] = {};
   const int dev = current_device();
-  if (smem > configured[dev][async]) {
+  const int which = ctas_per_sm == 3 ? 2 : (async ? 1 : 0);
+  if (smem > configured[dev][which]) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured[dev][async] = smem;
+    configured[dev][which] = smem;
   }
   const int grid = std::min(a.n_items, slots);
   kern<<<grid, TC_THREADS, smem, stream>>>(a);

@@ -7,6 +7,8 @@
 // (C=3 -> 3 active threads per block).  Here the loads are block-parallel and coalesced; the
 // sums that the reference defines sequentially (sec_mean's sum(x/count), global_avg_pool's
 // sum(x)/n) keep their sequential fp32 addition order, so results are bit-identical.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b2s {
@@ -100,6 +102,76 @@ __global__ void __launch_bounds__(SEG_THREADS)
     }
     __syncthreads();
   }
+}
+
+// Long segments (proposals of ~10k points): grid = (segment, part), every CTA scans one contiguous part of its segment
+// with the kernel above's thread layout and writes a partial (max, first arg-max) per channel; the combine kernel
+// merges the parts in order (ties keep the lower row: same result as one sequential scan, roipool.cu:22-30).
+__global__ void __launch_bounds__(SEG_THREADS)
+    seg_max_parts_kernel(const float* __restrict__ inp, const int32_t* __restrict__ offsets, float* __restrict__ pval,
+                         int32_t* __restrict__ pidx, int n_seg, int c, int parts) {
+  extern __shared__ unsigned char s_raw[];
+  const int cw = c < SEG_THREADS ? c : SEG_THREADS;
+  const int phases = SEG_THREADS / cw;
+  float* s_val = (float*)s_raw;
+  int32_t* s_idx = (int32_t*)(s_val + phases * c);
+  const int ch0 = threadIdx.x % cw, ph = threadIdx.x / cw;
+  const int seg = blockIdx.x, part = blockIdx.y;
+  const int b0 = offsets[seg], e0 = offsets[seg + 1];
+  const int per = (e0 - b0 + parts - 1) / parts;
+  const int b = b0 + part * per, e = min(e0, b + per);
+  if (ph < phases) {
+    for (int ch = ch0; ch < c; ch += cw) {
+      float best = -INFINITY;
+      int bi = -1;
+      for (int r = b + ph; r < e; r += phases) {
+        const float v = __ldg(inp + (int64_t)r * c + ch);
+        if (v > best) {
+          best = v;
+          bi = r;
+        }
+      }
+      s_val[ph * c + ch] = best;
+      s_idx[ph * c + ch] = bi;
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += SEG_THREADS) {
+    float best = -INFINITY;
+    int bi = -1;
+    for (int w = 0; w < phases; ++w) {
+      const float v = s_val[w * c + ch];
+      const int i = s_idx[w * c + ch];
+      if (i < 0) continue;
+      if (bi < 0 || v > best || (v == best && i < bi)) {
+        best = v;
+        bi = i;
+      }
+    }
+    pval[((int64_t)seg * parts + part) * c + ch] = best;
+    pidx[((int64_t)seg * parts + part) * c + ch] = bi;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    seg_max_combine_kernel(const float* __restrict__ pval, const int32_t* __restrict__ pidx, float* __restrict__ out,
+                           int32_t* __restrict__ argidx, int64_t total, int c, int parts) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int64_t seg = t / c;
+  const int ch = (int)(t - seg * c);
+  float best = -INFINITY;
+  int bi = -1;
+  for (int p = 0; p < parts; ++p) {  // parts are in row order: a strict > keeps the first maximum
+    const float v = pval[(seg * parts + p) * c + ch];
+    const int i = pidx[(seg * parts + p) * c + ch];
+    if (i >= 0 && (bi < 0 || v > best)) {
+      best = v;
+      bi = i;
+    }
+  }
+  out[t] = best;
+  if (argidx) argidx[t] = bi;
 }
 
 __global__ void __launch_bounds__(256)
@@ -422,6 +494,36 @@ int b2s_roipool_fp(const float* feats, const int32_t* offsets, float* out, int32
                    int32_t c, b2s_stream_t s) {
   return minmax(feats, offsets, out, maxidx, n_seg, c, 0, s);
 }
+size_t b2s_roipool_ws_bytes(int32_t n_seg, int32_t c) { return (size_t)(n_seg > 0 ? n_seg : 1) * 32 * c * 8 + 256; }
+
+// roipool forward for long segments: n_rows = rows of feats (picks the number of parts per segment); ws from
+// b2s_roipool_ws_bytes.  Same result as b2s_roipool_fp.
+int b2s_roipool_fp_ws(const float* feats, const int32_t* offsets, float* out, int32_t* maxidx, int32_t n_seg,
+                      int32_t c, int64_t n_rows, void* ws, size_t ws_bytes, b2s_stream_t stream) {
+  if (n_seg < 0 || c < 1 || c > 2048) {
+    set_error("roipool_fp_ws: invalid argument");
+    return B2S_E_INVALID;
+  }
+  if (n_seg == 0) return B2S_OK;
+  const int64_t avg = n_rows / n_seg;
+  int parts = (int)std::min<int64_t>(32, std::max<int64_t>(1, avg / 1024));
+  // enough CTAs to fill the GPU, no more parts than that needs
+  while (parts > 1 && (int64_t)n_seg * (parts / 2) >= 4 * (int64_t)sm_count()) parts /= 2;
+  if (parts <= 1 || ws == nullptr || ws_bytes < b2s_roipool_ws_bytes(n_seg, c))
+    return minmax(feats, offsets, out, maxidx, n_seg, c, 0, stream);
+  float* pval = (float*)ws;
+  int32_t* pidx = (int32_t*)((char*)ws + (size_t)n_seg * parts * c * 4);
+  const int cw = c < SEG_THREADS ? c : SEG_THREADS;
+  const size_t smem = (size_t)2 * (SEG_THREADS / cw) * c * 4;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(seg_max_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  seg_max_parts_kernel<<<dim3((unsigned)n_seg, (unsigned)parts), SEG_THREADS, smem, stream>>>(feats, offsets, pval, pidx,
+                                                                                              n_seg, c, parts);
+  const int64_t total = (int64_t)n_seg * c;
+  seg_max_combine_kernel<<<(unsigned)cdiv(total, 256), 256, 0, stream>>>(pval, pidx, out, maxidx, total, c, parts);
+  return check_launch("roipool_fp_ws");
+}
+
 int b2s_roipool_bp(float* d_feats, const int32_t* offsets, const int32_t* maxidx, const float* d_out,
                    int32_t n_seg, int32_t c, b2s_stream_t stream) {
   (void)offsets;

@@ -252,7 +252,10 @@ class GeneralModel(nn.Module):
                              data.get("voxel_level_sizes") if ASYNC_SIZES else None)
 
     def base_loss(self, data, out):
-        losses = {"semantic_loss": F.cross_entropy(out["semantic_scores"], data["sem_labels"].long(), ignore_index=-1)}
+        if out["semantic_scores"].is_cuda:  # fused libb2s kernels (torch's nll_loss reduction is one CTA: 0.67 ms)
+            losses = {"semantic_loss": ops.cross_entropy(out["semantic_scores"], data["sem_labels"], ignore_index=-1)}
+        else:
+            losses = {"semantic_loss": F.cross_entropy(out["semantic_scores"], data["sem_labels"].long(), ignore_index=-1)}
         gt_offsets = data["instance_center_xyz"] - data["point_xyz"]
         losses["offset_norm_loss"], losses["offset_dir_loss"] = pt_offset_loss(
             out["point_offsets"], gt_offsets, data["instance_ids"] != -1)
@@ -304,14 +307,18 @@ class PointGroup(GeneralModel):
         batch_offsets_ = torch.cumsum(torch.bincount(batch_idxs_ + 1), dim=0).int()
         coords_ = data["point_xyz"][object_idxs]
         sem_ = semantic_preds[object_idxs].contiguous()
-        sets = []
-        for xyz, mean_active in ((coords_.contiguous(), cfg.cluster_meanActive),
-                                 ((coords_ + offsets.detach()[object_idxs]).contiguous(), cfg.cluster_shift_meanActive)):
-            idx, start_len = common_ops.ballquery_batch_p(xyz, batch_idxs_, batch_offsets_, cfg.cluster_radius, mean_active)
-            p_idx, p_off = pointgroup_ops.pg_bfs_cluster(sem_, idx, start_len, cfg.cluster_npoint_thre)
-            p_idx = p_idx.long()
-            p_idx[:, 1] = object_idxs[p_idx[:, 1]]
-            sets.append((p_idx, p_off))
+        # both ball queries, then both BFS clusterings, each pair with ONE host read of its data-dependent sizes
+        # (the reference-shaped single calls -- common_ops.ballquery_batch_p / pointgroup_ops.pg_bfs_cluster -- read
+        # one count each; results are identical, tests/test_gpu_models.py)
+        with torch.no_grad():
+            shifted = (coords_ + offsets.detach()[object_idxs]).contiguous()
+            queries = ops.ballquery_many([coords_.contiguous(), shifted], batch_idxs_.contiguous(), batch_offsets_,
+                                         cfg.cluster_radius)
+            sets = []
+            for p_idx, p_off in ops.pg_cluster_many(sem_, queries, cfg.cluster_npoint_thre):
+                p_idx = p_idx.long()
+                p_idx[:, 1] = object_idxs[p_idx[:, 1]]
+                sets.append((p_idx, p_off))
         (p_idx, p_off), (s_idx, s_off) = sets  # unshifted first, shifted appended (pointgroup.py:70-73)
         s_idx[:, 0] += p_off.size(0) - 1
         proposals_idx = torch.cat((p_idx, s_idx), dim=0)

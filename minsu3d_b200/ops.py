@@ -535,6 +535,40 @@ def ballquery(coords, batch_idxs, batch_offsets, radius):
     return idx, start_len
 
 
+def ballquery_many(coord_sets, batch_idxs, batch_offsets, radius):
+    """Several ball queries over the same points' batch layout (PointGroup: raw and shifted coordinates,
+    pointgroup.py:43,58) with ONE host read for all pair counts instead of one per query: all count passes are
+    enqueued first (each keeps its own cell grid), the counts are read together, then all fill passes run.
+    Returns [(idx, start_len), ...], identical to [ballquery(c, ...) for c in coord_sets]."""
+    require_cuda(batch_idxs, batch_offsets, *coord_sets)
+    n = batch_idxs.numel()
+    dev = batch_idxs.device
+    nb = batch_offsets.numel() - 1
+    if n == 0:
+        return [ballquery(c, batch_idxs, batch_offsets, radius) for c in coord_sets]
+    ws_bytes = lib().b2s_ballquery_ws_bytes(n)
+    state = []
+    for qi, coords in enumerate(coord_sets):
+        require(coords.dtype == torch.float32 and coords.is_contiguous() and tuple(coords.shape) == (n, 3),
+                "coords must be contiguous float32 [n,3]")
+        start_len = torch.empty((n, 2), dtype=I32, device=dev)
+        d_count = _dev_i32(1, dev)
+        ws = workspace(ws_bytes, dev, slot=1 + qi)  # private: the cell grid must survive until the fill
+        check(lib().b2s_ballquery_count(ptr(coords), ptr(batch_idxs), ptr(batch_offsets), n, nb, float(radius),
+                                        ptr(start_len), ptr(d_count), ptr(ws), ws.numel(), stream()), "ballquery_count")
+        state.append((coords, start_len, d_count, ws))
+    counts = torch.cat([st[2] for st in state]).tolist()
+    run_deferred_checks()
+    out = []
+    for (coords, start_len, _, ws), n_active in zip(state, counts):
+        idx = _dev_i32(n_active, dev)
+        if n_active > 0:
+            check(lib().b2s_ballquery_fill(ptr(coords), ptr(batch_idxs), ptr(batch_offsets), n, nb, float(radius),
+                                           ptr(start_len), ptr(idx), ptr(ws), ws.numel(), stream()), "ballquery_fill")
+        out.append((idx, start_len))
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # C2 / C3 / C4 clustering
 # ------------------------------------------------------------------------------------------
@@ -573,6 +607,40 @@ def cluster_extract(nbr_idx, start_len, labels, comp, mode, thr_i=0, thr_f=0.0, 
                                       ptr(seeds), n_cluster, ptr(cluster_idxs), ptr(ws), ws.numel(), stream()),
               "cluster_order")
     return cluster_idxs, offsets
+
+
+def pg_cluster_many(labels, queries, threshold):
+    """pg_bfs_cluster (mode 0) on several ball-query results over the same labelled points with ONE host read for all
+    (nCluster, sumNPoint) pairs: label + select of every query are enqueued first (private scratch each), the counts
+    are read together, then the BFS orders run.  Returns [(cluster_idxs, cluster_offsets), ...]."""
+    require_cuda(labels)
+    n = labels.numel()
+    dev = labels.device
+    ws_bytes = lib().b2s_cluster_ws_bytes(n)
+    state = []
+    for qi, (nbr_idx, start_len) in enumerate(queries):
+        comp = _dev_i32(n, dev)
+        ws = workspace(ws_bytes, dev, slot=1 + qi)
+        check(lib().b2s_cluster_label(ptr(nbr_idx), ptr(start_len), ptr(labels), n, ptr(comp), ptr(ws), ws.numel(),
+                                      stream()), "cluster_label")
+        offsets = _dev_i32(n + 1, dev)
+        seeds = _dev_i32(max(n, 1), dev)
+        d_count = _dev_i32(2, dev)
+        check(lib().b2s_cluster_select(ptr(comp), ptr(labels), n, 0, int(threshold), 0.0, None, 0, ptr(offsets),
+                                       ptr(seeds), ptr(d_count), ptr(ws), ws.numel(), stream()), "cluster_select")
+        state.append((nbr_idx, start_len, comp, offsets, seeds, d_count, ws))
+    counts = torch.stack([st[5] for st in state]).tolist()
+    run_deferred_checks()
+    out = []
+    for (nbr_idx, start_len, comp, offsets, seeds, _, ws), (n_cluster, total) in zip(state, counts):
+        cluster_idxs = torch.empty((total, 2), dtype=I32, device=dev)
+        offsets = offsets[:n_cluster + 1]
+        if n_cluster > 0:
+            check(lib().b2s_cluster_order(ptr(nbr_idx), ptr(start_len), ptr(labels), ptr(comp), n, nbr_idx.numel(),
+                                          ptr(offsets), ptr(seeds), n_cluster, ptr(cluster_idxs), ptr(ws), ws.numel(),
+                                          stream()), "cluster_order")
+        out.append((cluster_idxs, offsets))
+    return out
 
 
 def cluster_centers(cluster_idxs, cluster_offsets, coords, labels, batch_idxs):
@@ -622,7 +690,10 @@ def sec_reduce(kind, inp, offsets, out):
 def roipool_fp(feats, offsets, out, maxidx):
     _f32c(feats, "feats")
     require(offsets.dtype == I32 and offsets.is_contiguous(), "offsets must be contiguous int32")
-    _seg("b2s_roipool_fp", feats, offsets, out, maxidx)
+    n_seg, c = offsets.numel() - 1, feats.size(1)
+    ws = workspace(lib().b2s_roipool_ws_bytes(n_seg, c), feats.device)
+    check(lib().b2s_roipool_fp_ws(ptr(feats), ptr(offsets), ptr(out), ptr(maxidx), n_seg, c, feats.size(0), ptr(ws),
+                                  ws.numel(), stream()), "roipool_fp")
 
 
 def roipool_bp(d_feats, offsets, maxidx, d_out):
@@ -655,6 +726,45 @@ def get_mask_label(proposals_idx, proposals_offset, instance_labels, instance_cl
     check(lib().b2s_get_mask_label(ptr(proposals_idx), ptr(proposals_offset), ptr(instance_labels),
                                    ptr(instance_cls), ptr(proposals_iou), n_inst, n_prop, int(ignored_label),
                                    float(iou_thr), ptr(mask_label), ptr(mask_label_mask), stream()), "get_mask_label")
+
+
+# ------------------------------------------------------------------------------------------
+# semantic cross-entropy of the train step (general_model.py:36-40)
+# ------------------------------------------------------------------------------------------
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, labels, ignore_index):
+        _f32c(scores, "scores")
+        require_cuda(labels)
+        require(labels.dtype in (torch.int16, torch.int64) and labels.is_contiguous() and labels.numel() == scores.size(0),
+                "labels must be contiguous int16 / int64 [n]")
+        n, c = scores.shape
+        out = torch.empty(2, dtype=torch.float32, device=scores.device)  # loss, n_valid
+        ws = workspace(lib().b2s_cross_entropy_ws_bytes(n), scores.device)
+        check(lib().b2s_cross_entropy_forward(ptr(scores), ptr(labels), labels.element_size(), n, c, int(ignore_index),
+                                              ptr(out), out.data_ptr() + 4, ptr(_bn_counter(scores.device)), ptr(ws),
+                                              ws.numel(), stream()), "cross_entropy_forward")
+        ctx.save_for_backward(scores, labels, out)
+        ctx.ignore_index = int(ignore_index)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        scores, labels, out = ctx.saved_tensors
+        n, c = scores.shape
+        g = torch.empty_like(scores)
+        gout = gout.contiguous().to(torch.float32).reshape(1)
+        check(lib().b2s_cross_entropy_backward(ptr(scores), ptr(labels), labels.element_size(), n, c, ctx.ignore_index,
+                                               out.data_ptr() + 4, ptr(gout), ptr(g), stream()), "cross_entropy_backward")
+        return g, None, None
+
+
+def cross_entropy(scores, labels, ignore_index=-1):
+    """F.cross_entropy(scores, labels.long(), ignore_index=ignore_index) (mean over the labelled rows) for float32
+    [n, c] CUDA scores and int16 / int64 labels, fused forward and backward kernels."""
+    if scores.size(0) == 0:
+        return torch.nn.functional.cross_entropy(scores, labels.long(), ignore_index=ignore_index)
+    return _CrossEntropy.apply(scores.contiguous(), labels.contiguous(), ignore_index)
 
 
 # ------------------------------------------------------------------------------------------

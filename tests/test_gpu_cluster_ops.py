@@ -263,6 +263,26 @@ def test_roipool_forward_backward(ref_ops):
     assert np.array_equal(xt2.grad.cpu().numpy(), oracle.gap_bp(x.shape[0], offs, g))
 
 
+@pytest.mark.parametrize("n_seg,max_len", [(72, 24_000), (5, 60_000), (400, 5_000)])
+def test_roipool_long_segments_multi_part_path(n_seg, max_len):
+    """Proposals of ~10k points (the bench batch: 72 proposals over ~700k point entries) take the multi-CTA-per-segment
+    path of b2s_roipool_fp_ws: values and FIRST arg-max (ties from rounding) bit-exact against the oracle, with an
+    empty segment in the middle."""
+    from minsu3d_b200.common_ops.functions import common_ops
+    rng = np.random.default_rng(n_seg)
+    offs = _segments(rng, n_seg, max_len, with_empty=True)
+    x = np.round(rng.standard_normal((offs[-1], 16)), 1).astype(np.float32)
+    want, arg = oracle.roipool_fp(x, offs)
+    xt = _dev(x).requires_grad_(True)
+    y = common_ops.roipool(xt, _dev(offs))
+    keep = np.diff(offs) > 0  # the oracle / reference leave an empty segment's row at its initial value
+    assert np.array_equal(y.detach().cpu().numpy()[keep], want[keep])
+    g = rng.standard_normal(want.shape).astype(np.float32)
+    g[~keep] = 0
+    y.backward(_dev(g))
+    assert np.array_equal(xt.grad.cpu().numpy(), oracle.roipool_bp(x.shape[0], arg, g))
+
+
 def test_segmented_empty_segments():
     from minsu3d_b200.common_ops.functions import common_ops
     x = torch.arange(12, dtype=torch.float32, device="cuda").view(4, 3)

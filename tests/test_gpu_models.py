@@ -312,3 +312,23 @@ def test_packed_weight_cache_follows_fused_optimizer_steps(batch):
     kmap = st.coordinate_manager.kernel_map(st.coordinate_map_key, st.coordinate_map_key, 3)
     assert torch.equal(conv(st).F.detach(), ops.conv_table(x, conv.kernel.detach(), kmap.nbr, kmap.n_out, 27, 16, 32,
                                                            tile_mask=kmap.tile_mask))
+
+
+@pytest.mark.parametrize("dtype", [torch.int16, torch.int64])
+def test_fused_cross_entropy_matches_torch(dtype):
+    """ops.cross_entropy (fused forward / backward kernels) vs F.cross_entropy(ignore_index=-1): loss to 1e-6
+    relative (double-precision block sums vs torch's float accumulation), gradient to 1e-6 absolute of its scale."""
+    from minsu3d_b200 import ops
+    torch.manual_seed(3)
+    n, c = 123_457, 20
+    x = (torch.randn(n, c, device="cuda") * 3).requires_grad_(True)
+    lab = torch.randint(-1, c, (n,), device="cuda").to(dtype)
+    want = torch.nn.functional.cross_entropy(x, lab.long(), ignore_index=-1)
+    (want * 1.7).backward()
+    gw = x.grad.clone()
+    x.grad = None
+    got = ops.cross_entropy(x, lab, ignore_index=-1)
+    (got * 1.7).backward()
+    assert abs(float(got) - float(want)) < 1e-6 * abs(float(want))
+    assert float((x.grad - gw).abs().max()) < 1e-6 * float(gw.abs().max()) + 1e-12
+    assert torch.equal(ops.cross_entropy(x.detach(), lab), ops.cross_entropy(x.detach(), lab))  # deterministic
