@@ -7,6 +7,9 @@ namespace b2s {
 int conv_table_simt(const float*, const float*, const int32_t*, float*, int64_t, int, int, int, int, int, cudaStream_t);
 int conv_pairs_simt(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, float*, int, int, int, int, int64_t, cudaStream_t);
 int conv_wgrad_simt(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, float*, int, int, int, int64_t, cudaStream_t);
+// weight gradient on the tensor cores (wgrad_mma.cu: mma.sync m16n8k8 3xTF32)
+bool conv_wgrad_mma_supported(int c_a, int c_g);
+int conv_wgrad_mma(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, float*, int, int, int, int64_t, cudaStream_t);
 // tcgen05 paths (conv_tc.cu: per-tile kernel, PAIRS mode + fallback; conv_tcp.cu: persistent table kernel)
 bool conv_tc_supported(int K, int c_in, int c_out);
 size_t conv_tc_ws_bytes(int K, int c_in, int c_out);
@@ -178,7 +181,13 @@ int b2s_conv_wgrad(const float* A, const float* G, const int32_t* src, const int
     set_error("conv_wgrad: invalid argument");
     return B2S_E_INVALID;
   }
-  (void)algo;
+  // algo 1 = fp32 FMA (strict); otherwise the tensor-core kernel when the channel counts allow (B2S_WGRAD_MMA=0 turns it off)
+  static const int mma_on = [] {
+    const char* e = getenv("B2S_WGRAD_MMA");
+    return (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }();
+  if (algo != 1 && mma_on && conv_wgrad_mma_supported(c_a, c_g))
+    return conv_wgrad_mma(A, G, src, dst, k_offsets, gW, K, c_a, c_g, max_pairs, stream);
   return conv_wgrad_simt(A, G, src, dst, k_offsets, gW, K, c_a, c_g, max_pairs, stream);
 }
 

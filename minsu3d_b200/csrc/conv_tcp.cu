@@ -79,9 +79,6 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// MINCTAS: CTAs per SM the register allocation aims for.  3 (narrow layers: c_out <= 32 -> 128 TMEM columns, <= 75 KB of
-// shared memory) puts 18 warps on an SM instead of 12: the gather is latency-bound (see above), more resident warps are
-// the one remedy that costs no extra instructions.
 template <int NSPLIT, bool ASYNC>
 __device__ __forceinline__ void conv_tcp_body(const TcpArgs& a) {
   extern __shared__ uint8_t smem_raw[];
@@ -547,7 +544,10 @@ __device__ __forceinline__ void conv_tcp_body(const TcpArgs& a) {
   }
 }
 
-// entry points: 2 CTAs/SM (up to 168 registers) and 3 CTAs/SM (112 registers: 3 x 192 x 112 = 64,512)
+// entry points: 2 CTAs/SM (up to 168 registers, the default) and 3 CTAs/SM (112 registers, 8 bytes of spills;
+// B2S_TC_CTAS=3, narrow layers only).  The 3-CTA variant was MEASURED SLOWER on the level-0 map -- 16->16 cold 87.7 us vs
+// 68.9 us, step 27.6 vs 26.0 ms (profiles/r02_conv_tcp_variants.txt) -- with three stages, a streamed instead of
+// resident weight set and 50 % more gather streams contending for the same L1TEX; it stays as an experiment switch.
 template <int NSPLIT, bool ASYNC>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tcp_kernel(const TcpArgs a) {
   conv_tcp_body<NSPLIT, ASYNC>(a);
@@ -598,7 +598,7 @@ static int launch_tcp(TcpArgs a, void* split_ws, float* final_out, const float* 
   // 512 columns per SM: <= 128 per CTA lets three CTAs share an SM, <= 256 two, more only one
   auto fits = [&](int ab, int S, int cap) { return ab * a.c_out + S * a_cols <= cap; };
   int cap = 256, ab = 2;
-  const bool allow3 = tcp_env("B2S_TC_CTAS", 3) >= 3;
+  const bool allow3 = tcp_env("B2S_TC_CTAS", 2) >= 3;  // measured slower (see conv_tcp3_kernel): off by default
   if (allow3 && fits(2, 3, 128)) {
     cap = 128;
     ab = 2;
