@@ -147,6 +147,14 @@ int b2s_conv_pairs(const float* A, const float* W, const float* Wp, const int32_
 int b2s_conv_wgrad(const float* A, const float* G, const int32_t* src, const int32_t* dst,
                    const int32_t* k_offsets, float* gW, int32_t K, int32_t c_a, int32_t c_g,
                    int64_t max_pairs, int32_t algo, b2s_stream_t stream);
+/* The same product with a caller workspace of b2s_conv_wgrad_ws_bytes(K, c_a, c_g) bytes (independent of the pair
+ * count).  With channel counts that are multiples of 16 (and algo != 1) it runs the deterministic tensor-core kernel
+ * (csrc/wgrad_det.cu): per-warp partial tiles in the workspace, summed in a fixed order -- no atomics, the same bits
+ * on every run; other shapes fall through to b2s_conv_wgrad.                                                     */
+size_t b2s_conv_wgrad_ws_bytes(int32_t K, int32_t c_a, int32_t c_g);
+int b2s_conv_wgrad_ws(const float* A, const float* G, const int32_t* src, const int32_t* dst,
+                      const int32_t* k_offsets, float* gW, int32_t K, int32_t c_a, int32_t c_g, int64_t max_pairs,
+                      int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * T5 -- fused BatchNorm(+ReLU) on sparse-tensor features (MinkowskiBatchNorm + MinkowskiReLU,

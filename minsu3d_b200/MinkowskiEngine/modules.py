@@ -572,7 +572,7 @@ class _BnReluConvFn(torch.autograd.Function):
         tmp = torch.empty((n_x, cin), dtype=torch.float32, device=dev)
         pin, pout, koff, maxp = kmap.pairs()
         c = max(cin, cout)
-        ws = ops.workspace(ops.resblock_ws_bytes(K, c, c), dev)
+        ws = ops.workspace(max(ops.resblock_ws_bytes(K, c, c), ops.wgrad_ws_bytes(K, cin, cout) + ops.lib().b2s_bn_ws_bytes(0, c) + 1024), dev)
         ops.check(ops.lib().b2s_bnconv_backward(
             gout.data_ptr(), x.data_ptr(), p_y, p_s, gamma.data_ptr(), kernel.data_ptr(), ops.ptr(ctx.packed), n_x, cin,
             cout, mode,

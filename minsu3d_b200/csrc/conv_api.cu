@@ -1,4 +1,5 @@
 // C-ABI dispatch for the sparse convolution products (b2s.h: T3 / T4).
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -10,6 +11,11 @@ int conv_wgrad_simt(const float*, const float*, const int32_t*, const int32_t*, 
 // weight gradient on the tensor cores (wgrad_mma.cu: mma.sync m16n8k8 3xTF32)
 bool conv_wgrad_mma_supported(int c_a, int c_g);
 int conv_wgrad_mma(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, float*, int, int, int, int64_t, cudaStream_t);
+// deterministic warp-stream kernel (wgrad_det.cu: mma.sync 3xTF32 straight from the gathered rows, partials + ordered sum)
+bool conv_wgrad_det_supported(int K, int c_a, int c_g);
+size_t conv_wgrad_det_ws_bytes(int K, int c_a, int c_g);
+int conv_wgrad_det(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, float*, int, int, int, int64_t,
+                   void*, size_t, cudaStream_t);
 // tcgen05 paths (conv_tc.cu: per-tile kernel, PAIRS mode + fallback; conv_tcp.cu: persistent table kernel)
 bool conv_tc_supported(int K, int c_in, int c_out);
 size_t conv_tc_ws_bytes(int K, int c_in, int c_out);
@@ -189,6 +195,28 @@ int b2s_conv_wgrad(const float* A, const float* G, const int32_t* src, const int
   if (algo != 1 && mma_on && conv_wgrad_mma_supported(c_a, c_g))
     return conv_wgrad_mma(A, G, src, dst, k_offsets, gW, K, c_a, c_g, max_pairs, stream);
   return conv_wgrad_simt(A, G, src, dst, k_offsets, gW, K, c_a, c_g, max_pairs, stream);
+}
+
+size_t b2s_conv_wgrad_ws_bytes(int32_t K, int32_t c_a, int32_t c_g) {
+  return std::max<size_t>(conv_wgrad_det_ws_bytes(K, c_a, c_g), 256);
+}
+
+int b2s_conv_wgrad_ws(const float* A, const float* G, const int32_t* src, const int32_t* dst,
+                      const int32_t* k_offsets, float* gW, int32_t K, int32_t c_a, int32_t c_g, int64_t max_pairs,
+                      int32_t algo, void* ws, size_t ws_bytes, b2s_stream_t stream) {
+  if (K < 1 || K > 125 || c_a < 1 || c_g < 1 || max_pairs < 0) {
+    set_error("conv_wgrad: invalid argument");
+    return B2S_E_INVALID;
+  }
+  // algo 1 = fp32 FMA (strict); otherwise the deterministic tensor-core kernel when the channel counts are multiples
+  // of 16 (B2S_WGRAD_DET=0: the round-2 shared-memory kernels with their atomicAdd flush, kept for comparison)
+  static const int det_on = [] {
+    const char* e = getenv("B2S_WGRAD_DET");
+    return (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }();
+  if (algo != 1 && det_on && conv_wgrad_det_supported(K, c_a, c_g))
+    return conv_wgrad_det(A, G, src, dst, k_offsets, gW, K, c_a, c_g, max_pairs, ws, ws_bytes, stream);
+  return b2s_conv_wgrad(A, G, src, dst, k_offsets, gW, K, c_a, c_g, max_pairs, algo, stream);
 }
 
 }  // extern "C"

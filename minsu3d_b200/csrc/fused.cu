@@ -57,6 +57,12 @@ size_t b2s_resblock_ws_bytes(int32_t K, int32_t c_in, int32_t c_out) {
     const size_t b = b2s_conv_ws_bytes(s[0], s[1], s[2]);
     conv = b > conv ? b : conv;
   }
+  // the weight-gradient partials share the convolution scratch (same stream, one after the other)
+  const int wshapes[5][3] = {{K, c_in, c_out}, {K, c_out, c_out}, {K, c_out, c_in}, {K, c_in, c_in}, {1, c_in, c_out}};
+  for (const auto& s : wshapes) {
+    const size_t b = b2s_conv_wgrad_ws_bytes(s[0], s[1], s[2]);
+    conv = b > conv ? b : conv;
+  }
   return align_up(b2s_bn_ws_bytes(0, c)) + align_up(conv) + 1024;
 }
 
@@ -126,13 +132,15 @@ int b2s_resblock_backward(const float* gout, const float* x, const float* y1, co
   const Tables t{nbr, tile_mask, nbr_sorted, tile_mask_sorted, row_perm, K};
   // second convolution: data gradient (symmetric map: reversed offsets, transposed weights) and weight gradient
   B2S_TRY(conv_same(gout, W2, Wp2, nullptr, tmp_a, n, c_out, c_out, 1, 1, algo, t, conv_ws, conv_bytes, stream));
-  B2S_TRY(b2s_conv_wgrad(y2, gout, pair_in, pair_out, k_offsets, gW2, K, c_out, c_out, max_pairs, algo, stream));
+  B2S_TRY(b2s_conv_wgrad_ws(y2, gout, pair_in, pair_out, k_offsets, gW2, K, c_out, c_out, max_pairs, algo, conv_ws,
+                            conv_bytes, stream));
   // bn2 + relu
   B2S_TRY(b2s_bn_backward(z1, y2, tmp_a, n, c_out, stats2, stats2 + c_out, gamma2, 1, 1, tmp_b, dgb2, dgb2 + c_out,
                           bn_counter, bn_ws, bn_bytes, stream));
   // first convolution
   B2S_TRY(conv_same(tmp_b, W1, Wp1, nullptr, tmp_c, n, c_out, c_in, 1, 1, algo, t, conv_ws, conv_bytes, stream));
-  B2S_TRY(b2s_conv_wgrad(y1, tmp_b, pair_in, pair_out, k_offsets, gW1, K, c_in, c_out, max_pairs, algo, stream));
+  B2S_TRY(b2s_conv_wgrad_ws(y1, tmp_b, pair_in, pair_out, k_offsets, gW1, K, c_in, c_out, max_pairs, algo, conv_ws,
+                            conv_bytes, stream));
   // bn1 + relu, with the gradient that arrives over the shortcut added in the same pass: gout itself (identity
   // shortcut) or gout @ Wds^T (1x1 convolution; computed first into tmp_a, which is free again by now)
   const float* shortcut_grad = gout;
@@ -143,7 +151,8 @@ int b2s_resblock_backward(const float* gout, const float* x, const float* y1, co
   }
   B2S_TRY(b2s_bn_backward_add(x, y1, tmp_c, shortcut_grad, n, c_in, stats1, stats1 + c_in, gamma1, 1, 1, gx, dgb1,
                               dgb1 + c_in, bn_counter, bn_ws, bn_bytes, stream));
-  if (Wds != nullptr) return b2s_conv_wgrad(x, gout, ident, ident, ident_koff, gWds, 1, c_in, c_out, n, algo, stream);
+  if (Wds != nullptr)
+    return b2s_conv_wgrad_ws(x, gout, ident, ident, ident_koff, gWds, 1, c_in, c_out, n, algo, conv_ws, conv_bytes, stream);
   return B2S_OK;
 }
 
@@ -209,11 +218,13 @@ int b2s_bnconv_backward(const float* gout, const float* x, const float* y, const
     // every fine row has exactly one (coarse row, offset): plain stores, no accumulation
     B2S_TRY(b2s_conv_pairs(gout, W, Wp, pair_out, pair_in, k_offsets, tmp, K, c_out, c_in, 1, max_pairs, algo, conv_ws,
                            conv_bytes, stream));
-    B2S_TRY(b2s_conv_wgrad(y, gout, pair_in, pair_out, k_offsets, gW, K, c_in, c_out, max_pairs, algo, stream));
+    B2S_TRY(b2s_conv_wgrad_ws(y, gout, pair_in, pair_out, k_offsets, gW, K, c_in, c_out, max_pairs, algo, conv_ws,
+                              conv_bytes, stream));
   } else {
     B2S_TRY(b2s_conv_table(gout, W, Wp, nbr, tile_mask, nullptr, tmp, n_coarse, K, c_out, c_in, 1, 0, algo, conv_ws,
                            conv_bytes, stream));
-    B2S_TRY(b2s_conv_wgrad(y, gout, pair_out, pair_in, k_offsets, gW, K, c_in, c_out, max_pairs, algo, stream));
+    B2S_TRY(b2s_conv_wgrad_ws(y, gout, pair_out, pair_in, k_offsets, gW, K, c_in, c_out, max_pairs, algo, conv_ws,
+                              conv_bytes, stream));
   }
   return b2s_bn_backward(x, y, tmp, n_x, c_in, stats, stats + c_in, gamma, 1, 1, gx, dgb, dgb + c_in, bn_counter, bn_ws,
                          bn_bytes, stream);

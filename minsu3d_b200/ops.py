@@ -386,9 +386,22 @@ def conv_wgrad(A, G, src, dst, k_offsets, K, c_a, c_g, max_pairs, algo=None):
     _f32c(A, "A")
     _f32c(G, "G")
     gW = torch.empty((K, c_a, c_g), dtype=torch.float32, device=A.device)
-    check(lib().b2s_conv_wgrad(ptr(A), ptr(G), ptr(src), ptr(dst), ptr(k_offsets), ptr(gW), K, c_a, c_g,
-                               int(max_pairs), _default_algo if algo is None else algo, stream()), "conv_wgrad")
+    ws = workspace(wgrad_ws_bytes(K, c_a, c_g), A.device)
+    check(lib().b2s_conv_wgrad_ws(ptr(A), ptr(G), ptr(src), ptr(dst), ptr(k_offsets), ptr(gW), K, c_a, c_g,
+                                  int(max_pairs), _default_algo if algo is None else algo, ptr(ws), ws.numel(),
+                                  stream()), "conv_wgrad")
     return gW
+
+
+_WGRAD_WS = {}
+
+
+def wgrad_ws_bytes(K, c_a, c_g):
+    key = (K, c_a, c_g)
+    v = _WGRAD_WS.get(key)
+    if v is None:
+        v = _WGRAD_WS[key] = lib().b2s_conv_wgrad_ws_bytes(K, c_a, c_g)
+    return v
 
 
 # ------------------------------------------------------------------------------------------

@@ -150,6 +150,66 @@ def test_conv3_forward_backward(cin, cout, algo_name):
     _close(gw, want_gw)
 
 
+WGRAD_SHAPES = [(16, 16), (32, 16), (16, 32), (32, 32), (48, 32), (48, 48), (64, 64), (80, 80), (96, 112), (224, 112),
+                (128, 256)]
+
+
+@pytest.mark.parametrize("ca,cg", WGRAD_SHAPES)
+def test_wgrad_deterministic_kernel(ca, cg):
+    """T3 weight gradient, default path for channel counts that are multiples of 16 (csrc/wgrad_det.cu, mma.sync
+    3xTF32 straight from the gathered rows): 1e-4 of max-abs vs the oracle for every register tiling incl. ragged
+    channel tiles, and bit-identical results run to run (per-warp partials summed in a fixed order, no atomics)."""
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(ca * 1000 + cg)
+    n = 3000 if ca * cg > 4096 else 20_000
+    c = surface_voxels(rng, n)
+    n = c.shape[0]
+    nbr = oracle.kernel_map(c, c, 3, 1)
+    x = rng.standard_normal((n, ca)).astype(np.float32)
+    w = np.zeros((27, ca, cg), np.float32)
+    g = rng.standard_normal((n, cg)).astype(np.float32)
+    _, want_gw = oracle.conv_bwd(x, w, g, nbr)
+    pin, pout, koff, _ = ops.pairs_from_nbr(_dev(nbr))
+    gw = ops.conv_wgrad(_dev(x), _dev(g), pin, pout, koff, 27, ca, cg, n * 27, algo=ops.ALGO_TC_3XTF32)
+    _close(gw, want_gw)
+    again = ops.conv_wgrad(_dev(x), _dev(g), pin, pout, koff, 27, ca, cg, n * 27, algo=ops.ALGO_TC_3XTF32)
+    assert torch.equal(gw, again)
+    # exact pair count instead of the n*K bound: a different warp split, same sums within tolerance
+    exact = int(koff[-1].item())
+    _close(ops.conv_wgrad(_dev(x), _dev(g), pin, pout, koff, 27, ca, cg, exact, algo=ops.ALGO_TC_3XTF32), want_gw)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 129, 1000])
+def test_wgrad_deterministic_small_and_identity(n):
+    """Edge cases: empty / one-row maps (most offsets have no pair) and the K = 1 identity map of a 1x1 convolution."""
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(n)
+    ca, cg = 32, 48
+    if n:
+        c = surface_voxels(rng, n)
+        n = c.shape[0]
+        nbr = oracle.kernel_map(c, c, 3, 1)
+    else:
+        nbr = np.zeros((0, 27), np.int32)
+    x = rng.standard_normal((n, ca)).astype(np.float32)
+    g = rng.standard_normal((n, cg)).astype(np.float32)
+    pin, pout, koff, _ = ops.pairs_from_nbr(_dev(nbr))
+    gw = ops.conv_wgrad(_dev(x), _dev(g), pin, pout, koff, 27, ca, cg, n * 27)
+    if n:
+        _, want = oracle.conv_bwd(x, np.zeros((27, ca, cg), np.float32), g, nbr)
+        _close(gw, want)
+    else:
+        assert float(gw.abs().max()) == 0.0
+    ident = torch.arange(n, dtype=torch.int32, device="cuda")
+    koff1 = torch.tensor([0, n], dtype=torch.int32, device="cuda")
+    gw1 = ops.conv_wgrad(_dev(x), _dev(g), ident, ident, koff1, 1, ca, cg, n)
+    want1 = x.astype(np.float64).T @ g.astype(np.float64)
+    if n:
+        _close(gw1[0], want1)
+    else:
+        assert float(gw1.abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("n", [1, 100, 5000, 150_000])
 def test_tile_order_bit_exact(n):
     """Mask-sorted tile schedule: permutation, permuted table and tile masks equal the numpy restatement."""

@@ -1,4 +1,4 @@
-"""ncu target: weight-gradient kernels on the level-0 map (16x16) and a level-3-like map (64x64)."""
+"""ncu target: weight-gradient kernel on chosen shapes.  usage: wgrad_ncu_target.py rows:ca:cg [rows:ca:cg ...]"""
 import os
 import sys
 
@@ -8,29 +8,23 @@ import numpy as np
 import torch
 from helpers import surface_voxels
 from minsu3d_b200 import ops
-from minsu3d_b200.harness import scenes
 
-batch = scenes.make_batch([0, 1, 2, 3], "cuda", 100_000)
-table, _, _, oc = ops.coord_unique(batch["voxel_xyz"], 1)
-cases = [(oc, table, 16)]
 rng = np.random.default_rng(0)
-co = torch.from_numpy(surface_voxels(rng, 10_000, batch=4)).cuda()
-t2, _, _, oc2 = ops.coord_unique(co, 1)
-cases.append((oc2, t2, 64))
 work = []
-for c_, t_, ch in cases:
-    nbr = ops.kernel_map(c_, t_, 3, 1)
+for spec in sys.argv[1:] or ["330000:16:16", "25000:64:64"]:
+    rows, ca, cg = (int(v) for v in spec.split(":"))
+    co = torch.from_numpy(surface_voxels(rng, rows, batch=4)).cuda()
+    t2, _, _, oc2 = ops.coord_unique(co, 1)
+    nbr = ops.kernel_map(oc2, t2, 3, 1)
     pin, pout, koff, _ = ops.pairs_from_nbr(nbr)
-    n = c_.size(0)
-    x = torch.randn(n, ch, device="cuda")
-    g = torch.randn(n, ch, device="cuda")
-    work.append((x, g, pin, pout, koff, ch, n))
+    n = oc2.size(0)
+    work.append((torch.randn(n, ca, device="cuda"), torch.randn(n, cg, device="cuda"), pin, pout, koff, ca, cg, n))
 for w in work:
     for _ in range(2):
-        ops.conv_wgrad(w[0], w[1], w[2], w[3], w[4], 27, w[5], w[5], w[6] * 27)
+        ops.conv_wgrad(w[0], w[1], w[2], w[3], w[4], 27, w[5], w[6], w[7] * 27)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
 for w in work:
-    ops.conv_wgrad(w[0], w[1], w[2], w[3], w[4], 27, w[5], w[5], w[6] * 27)
+    ops.conv_wgrad(w[0], w[1], w[2], w[3], w[4], 27, w[5], w[6], w[7] * 27)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
