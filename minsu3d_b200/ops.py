@@ -524,6 +524,47 @@ def devoxelize(feat, idx):
 # ------------------------------------------------------------------------------------------
 # C1 ball query
 # ------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------
+# fork / join over side streams: independent library call sequences (PointGroup's two ball queries and clusterings,
+# pointgroup.py:43-66) run concurrently -- the BFS order of one (latency-bound: three device-wide barriers per BFS
+# level) overlaps the union-find / list fill of the other (throughput-bound).  Outputs are allocated on the main
+# stream before the fork and main waits for every side stream before anything is returned, so the caching
+# allocator's stream-ordered reuse stays valid.  B2S_CLUSTER_STREAMS=0: everything on the current stream.
+# ------------------------------------------------------------------------------------------
+import contextlib
+import os
+
+_SIDE_STREAMS = {}
+_FORK_ON = os.environ.get("B2S_CLUSTER_STREAMS", "1") != "0"
+
+
+class _Fork:
+    def __init__(self, device, n):
+        self.main = torch.cuda.current_stream(device)
+        key = (device.index, self.main.cuda_stream)
+        pool = _SIDE_STREAMS.setdefault(key, [])
+        while _FORK_ON and len(pool) < n - 1:
+            pool.append((torch.cuda.Stream(device=device), torch.cuda.Event(), torch.cuda.Event()))
+        self.side = pool[:n - 1] if _FORK_ON else []
+
+    def begin(self):
+        for s, ev_fork, _ in self.side:
+            ev_fork.record(self.main)
+            s.wait_event(ev_fork)
+
+    def on(self, i):
+        """Context: item 0 stays on the main stream, item i > 0 runs on side stream i - 1."""
+        if i == 0 or not self.side:
+            return contextlib.nullcontext()
+        return torch.cuda.stream(self.side[i - 1][0])
+
+    def join(self):
+        for s, _, ev_join in self.side:
+            ev_join.record(s)
+            self.main.wait_event(ev_join)
+
+
+
 def ballquery(coords, batch_idxs, batch_offsets, radius):
     """Returns (idx[nActive] i32, start_len[n,2] i32); one host read of nActive."""
     require_cuda(coords, batch_idxs, batch_offsets)
@@ -561,24 +602,33 @@ def ballquery_many(coord_sets, batch_idxs, batch_offsets, radius):
         return [ballquery(c, batch_idxs, batch_offsets, radius) for c in coord_sets]
     ws_bytes = lib().b2s_ballquery_ws_bytes(n)
     state = []
+    fork = _Fork(dev, len(coord_sets))
+    fork.begin()
     for qi, coords in enumerate(coord_sets):
         require(coords.dtype == torch.float32 and coords.is_contiguous() and tuple(coords.shape) == (n, 3),
                 "coords must be contiguous float32 [n,3]")
         start_len = torch.empty((n, 2), dtype=I32, device=dev)
         d_count = _dev_i32(1, dev)
-        ws = workspace(ws_bytes, dev, slot=1 + qi)  # private: the cell grid must survive until the fill
-        check(lib().b2s_ballquery_count(ptr(coords), ptr(batch_idxs), ptr(batch_offsets), n, nb, float(radius),
-                                        ptr(start_len), ptr(d_count), ptr(ws), ws.numel(), stream()), "ballquery_count")
+        with fork.on(qi):
+            ws = workspace(ws_bytes, dev, slot=1 + qi)  # private: the cell grid must survive until the fill
+            check(lib().b2s_ballquery_count(ptr(coords), ptr(batch_idxs), ptr(batch_offsets), n, nb, float(radius),
+                                            ptr(start_len), ptr(d_count), ptr(ws), ws.numel(), stream()),
+                  "ballquery_count")
         state.append((coords, start_len, d_count, ws))
+    fork.join()
     counts = torch.cat([st[2] for st in state]).tolist()
     run_deferred_checks()
     out = []
-    for (coords, start_len, _, ws), n_active in zip(state, counts):
+    fork.begin()
+    for qi, ((coords, start_len, _, ws), n_active) in enumerate(zip(state, counts)):
         idx = _dev_i32(n_active, dev)
         if n_active > 0:
-            check(lib().b2s_ballquery_fill(ptr(coords), ptr(batch_idxs), ptr(batch_offsets), n, nb, float(radius),
-                                           ptr(start_len), ptr(idx), ptr(ws), ws.numel(), stream()), "ballquery_fill")
+            with fork.on(qi):
+                check(lib().b2s_ballquery_fill(ptr(coords), ptr(batch_idxs), ptr(batch_offsets), n, nb, float(radius),
+                                               ptr(start_len), ptr(idx), ptr(ws), ws.numel(), stream()),
+                      "ballquery_fill")
         out.append((idx, start_len))
+    fork.join()
     return out
 
 
@@ -631,28 +681,35 @@ def pg_cluster_many(labels, queries, threshold):
     dev = labels.device
     ws_bytes = lib().b2s_cluster_ws_bytes(n)
     state = []
+    fork = _Fork(dev, len(queries))
+    fork.begin()
     for qi, (nbr_idx, start_len) in enumerate(queries):
         comp = _dev_i32(n, dev)
-        ws = workspace(ws_bytes, dev, slot=1 + qi)
-        check(lib().b2s_cluster_label(ptr(nbr_idx), ptr(start_len), ptr(labels), n, ptr(comp), ptr(ws), ws.numel(),
-                                      stream()), "cluster_label")
         offsets = _dev_i32(n + 1, dev)
         seeds = _dev_i32(max(n, 1), dev)
         d_count = _dev_i32(2, dev)
-        check(lib().b2s_cluster_select(ptr(comp), ptr(labels), n, 0, int(threshold), 0.0, None, 0, ptr(offsets),
-                                       ptr(seeds), ptr(d_count), ptr(ws), ws.numel(), stream()), "cluster_select")
+        with fork.on(qi):
+            ws = workspace(ws_bytes, dev, slot=1 + qi)
+            check(lib().b2s_cluster_label(ptr(nbr_idx), ptr(start_len), ptr(labels), n, ptr(comp), ptr(ws), ws.numel(),
+                                          stream()), "cluster_label")
+            check(lib().b2s_cluster_select(ptr(comp), ptr(labels), n, 0, int(threshold), 0.0, None, 0, ptr(offsets),
+                                           ptr(seeds), ptr(d_count), ptr(ws), ws.numel(), stream()), "cluster_select")
         state.append((nbr_idx, start_len, comp, offsets, seeds, d_count, ws))
+    fork.join()
     counts = torch.stack([st[5] for st in state]).tolist()
     run_deferred_checks()
     out = []
-    for (nbr_idx, start_len, comp, offsets, seeds, _, ws), (n_cluster, total) in zip(state, counts):
+    fork.begin()
+    for qi, ((nbr_idx, start_len, comp, offsets, seeds, _, ws), (n_cluster, total)) in enumerate(zip(state, counts)):
         cluster_idxs = torch.empty((total, 2), dtype=I32, device=dev)
         offsets = offsets[:n_cluster + 1]
         if n_cluster > 0:
-            check(lib().b2s_cluster_order(ptr(nbr_idx), ptr(start_len), ptr(labels), ptr(comp), n, nbr_idx.numel(),
-                                          ptr(offsets), ptr(seeds), n_cluster, ptr(cluster_idxs), ptr(ws), ws.numel(),
-                                          stream()), "cluster_order")
+            with fork.on(qi):
+                check(lib().b2s_cluster_order(ptr(nbr_idx), ptr(start_len), ptr(labels), ptr(comp), n, nbr_idx.numel(),
+                                              ptr(offsets), ptr(seeds), n_cluster, ptr(cluster_idxs), ptr(ws),
+                                              ws.numel(), stream()), "cluster_order")
         out.append((cluster_idxs, offsets))
+    fork.join()
     return out
 
 
