@@ -92,29 +92,35 @@ __device__ __forceinline__ void wd_split(const int32_t* __restrict__ k_offsets, 
 // N consecutive floats (N in {2, 4, 6, 8}) as the widest loads the alignment allows; zeros when row < 0 or past the
 // channel count (cols_left = channels from the lane's first column to the end; vectors are all in or all out because
 // channel counts are multiples of 16)
-template <int N>
+template <int N, bool RAG>
 __device__ __forceinline__ void wd_load(float (&x)[N], const float* __restrict__ base, int row, int ld, int cols_left) {
-  constexpr int V = (N % 4 == 0) ? 4 : 2;
   const float* p = base + (int64_t)row * ld;
+  if constexpr (RAG) {
+    // any channel count (3-channel input convolution, 20-class linear head): scalar loads, guarded one by one
 #pragma unroll
-  for (int v = 0; v < N / V; ++v) {
-    if (row >= 0 && V * v < cols_left) {
-      if constexpr (V == 4) {
-        const float4 t = __ldg((const float4*)p + v);
-        x[4 * v] = t.x, x[4 * v + 1] = t.y, x[4 * v + 2] = t.z, x[4 * v + 3] = t.w;
+    for (int v = 0; v < N; ++v) x[v] = (row >= 0 && v < cols_left) ? __ldg(p + v) : 0.f;
+  } else {
+    constexpr int V = (N % 4 == 0) ? 4 : 2;
+#pragma unroll
+    for (int v = 0; v < N / V; ++v) {
+      if (row >= 0 && V * v < cols_left) {
+        if constexpr (V == 4) {
+          const float4 t = __ldg((const float4*)p + v);
+          x[4 * v] = t.x, x[4 * v + 1] = t.y, x[4 * v + 2] = t.z, x[4 * v + 3] = t.w;
+        } else {
+          const float2 t = __ldg((const float2*)p + v);
+          x[2 * v] = t.x, x[2 * v + 1] = t.y;
+        }
       } else {
-        const float2 t = __ldg((const float2*)p + v);
-        x[2 * v] = t.x, x[2 * v + 1] = t.y;
-      }
-    } else {
 #pragma unroll
-      for (int e = 0; e < V; ++e) x[V * v + e] = 0.f;
+        for (int e = 0; e < V; ++e) x[V * v + e] = 0.f;
+      }
     }
   }
 }
 
 // MT x NT m16n8 tiles per warp (channel tile 16*MT x 8*NT); KB k-steps per register buffer; U*32 pairs per chunk
-template <int MT, int NT, int KB, int U>
+template <int MT, int NT, int KB, int U, bool RAG>
 __global__ void __launch_bounds__(WD_THREADS, (MT * NT <= 8) ? 2 : 1)
     wgrad_det_kernel(const float* __restrict__ A, const float* __restrict__ G, const int32_t* __restrict__ src,
                      const int32_t* __restrict__ dst, const int32_t* __restrict__ k_offsets, float* __restrict__ part,
@@ -186,10 +192,10 @@ __global__ void __launch_bounds__(WD_THREADS, (MT * NT <= 8) ? 2 : 1)
       const int u = s >> 2, l0 = 8 * (s & 3) + tq;
       const int ra0 = __shfl_sync(0xffffffffu, is[u], l0), ra1 = __shfl_sync(0xffffffffu, is[u], l0 + 4);
       const int rg0 = __shfl_sync(0xffffffffu, id[u], l0), rg1 = __shfl_sync(0xffffffffu, id[u], l0 + 4);
-      wd_load<NA>(xa[buf][t][0], Ab, ra0, c_a, a_left);
-      wd_load<NA>(xa[buf][t][1], Ab, ra1, c_a, a_left);
-      wd_load<NG>(xg[buf][t][0], Gb, rg0, c_g, g_left);
-      wd_load<NG>(xg[buf][t][1], Gb, rg1, c_g, g_left);
+      wd_load<NA, RAG>(xa[buf][t][0], Ab, ra0, c_a, a_left);
+      wd_load<NA, RAG>(xa[buf][t][1], Ab, ra1, c_a, a_left);
+      wd_load<NG, RAG>(xg[buf][t][0], Gb, rg0, c_g, g_left);
+      wd_load<NG, RAG>(xg[buf][t][1], Gb, rg1, c_g, g_left);
     }
   };
   // (a term-major MMA order -- MT*NT independent accumulators between the three terms of one -- was measured slower:
@@ -308,6 +314,7 @@ __global__ void __launch_bounds__(WD_THREADS, (MT * NT <= 8) ? 2 : 1)
 
 struct WdShape {
   int mt, nt, ty, tz, B, u;
+  bool rag;
 };
 
 static int wd_pick(int units, int maxu) {  // units of 16 channels -> tiles of at most maxu units, as even as possible
@@ -328,10 +335,17 @@ static WdShape wd_shape(int K, int c_a, int c_g, int64_t max_pairs) {
   static const int env_maxu = wd_env("B2S_WGRAD_MAXT", 0);
   const int maxu = env_maxu > 0 ? std::min(4, env_maxu) : (max_pairs >= 400000 ? 4 : 2);
   WdShape s;
-  s.mt = c_a == 48 ? 3 : wd_pick(c_a / 16, maxu);
-  s.nt = c_g == 48 ? 6 : 2 * wd_pick(c_g / 16, maxu);
-  s.ty = (c_a / 16 + s.mt - 1) / s.mt;
-  s.tz = (c_g / 8 + s.nt - 1) / s.nt;
+  s.rag = (c_a % 16) != 0 || (c_g % 16) != 0;
+  const int ua = (c_a + 15) / 16, ug = (c_g + 15) / 16;
+  if (s.rag) {  // tiles up to 32 x 32 only (four instantiations)
+    s.mt = std::min(2, ua);
+    s.nt = 2 * std::min(2, ug);
+  } else {
+    s.mt = c_a == 48 ? 3 : wd_pick(ua, maxu);
+    s.nt = c_g == 48 ? 6 : 2 * wd_pick(ug, maxu);
+  }
+  s.ty = (ua + s.mt - 1) / s.mt;
+  s.tz = (2 * ug + s.nt - 1) / s.nt;
   const int prod = s.mt * s.nt;
   // CTAs over all channel tiles = one resident wave: 2 CTAs per SM up to 128 registers (tiles <= 32 x 32), else 1
   const int cap_total = sm_count() * (prod <= 8 ? 2 : 1);
@@ -346,8 +360,10 @@ static WdShape wd_shape(int K, int c_a, int c_g, int64_t max_pairs) {
   return s;
 }
 
+// channel counts that are multiples of 16 take the vector-load kernels; anything else up to 1024 channels the
+// element-guarded ("ragged") ones
 bool conv_wgrad_det_supported(int K, int c_a, int c_g) {
-  return K >= 1 && K <= WD_MAXK && c_a >= 16 && c_g >= 16 && (c_a % 16) == 0 && (c_g % 16) == 0;
+  return K >= 1 && K <= WD_MAXK && c_a >= 1 && c_g >= 1 && c_a <= 1024 && c_g <= 1024;
 }
 
 // upper bound over max_pairs (the CTA count is capped by the SM count)
@@ -361,12 +377,12 @@ size_t conv_wgrad_det_ws_bytes(int K, int c_a, int c_g) {
   return need + 256;
 }
 
-template <int MT, int NT, int KB, int U>
+template <int MT, int NT, int KB, int U, bool RAG>
 static int wd_launch(const WdShape& s, const float* A, const float* G, const int32_t* src, const int32_t* dst,
                      const int32_t* k_offsets, float* gW, float* part, int* done, int K, int c_a, int c_g,
                      cudaStream_t stream) {
   constexpr size_t smem = (size_t)4 * MT * NT * 128 * 4;
-  auto kern = wgrad_det_kernel<MT, NT, KB, U>;
+  auto kern = wgrad_det_kernel<MT, NT, KB, U, RAG>;
   static bool configured[B2S_MAX_DEVICES] = {};
   const int dev = current_device();
   if (smem + 2048 > 48 * 1024 && !configured[dev]) {
@@ -381,10 +397,19 @@ template <int MT, int NT, int KB4, int KB1>
 static int wd_dispatch(const WdShape& s, const float* A, const float* G, const int32_t* src, const int32_t* dst,
                        const int32_t* k_offsets, float* gW, float* part, int* done, int K, int c_a, int c_g,
                        cudaStream_t stream) {
-  if constexpr (MT * NT <= 8) {
-    if (s.u == 4) return wd_launch<MT, NT, KB4, 4>(s, A, G, src, dst, k_offsets, gW, part, done, K, c_a, c_g, stream);
+  if constexpr (MT <= 2 && NT <= 4) {
+    if (s.rag) {
+      constexpr int KBR = (MT * NT <= 2) ? 2 : 1;  // scalar loads hold more address registers: shorter batches
+      if (s.u == 4)
+        return wd_launch<MT, NT, KBR, 4, true>(s, A, G, src, dst, k_offsets, gW, part, done, K, c_a, c_g, stream);
+      return wd_launch<MT, NT, KBR, 1, true>(s, A, G, src, dst, k_offsets, gW, part, done, K, c_a, c_g, stream);
+    }
   }
-  return wd_launch<MT, NT, KB1, 1>(s, A, G, src, dst, k_offsets, gW, part, done, K, c_a, c_g, stream);
+  if constexpr (MT * NT <= 8) {
+    if (s.u == 4)
+      return wd_launch<MT, NT, KB4, 4, false>(s, A, G, src, dst, k_offsets, gW, part, done, K, c_a, c_g, stream);
+  }
+  return wd_launch<MT, NT, KB1, 1, false>(s, A, G, src, dst, k_offsets, gW, part, done, K, c_a, c_g, stream);
 }
 
 int conv_wgrad_det(const float* A, const float* G, const int32_t* src, const int32_t* dst, const int32_t* k_offsets,

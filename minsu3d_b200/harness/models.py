@@ -91,6 +91,13 @@ class UBlock(nn.Module):
         return out
 
 
+class PointLinear(nn.Linear):
+    """nn.Linear (same parameters / state-dict names) whose weight gradient over many points runs on libb2s."""
+
+    def forward(self, x):
+        return ops.linear(x, self.weight, self.bias)
+
+
 class Backbone(nn.Module):
     def __init__(self, input_channel, output_channel, block_channels, block_reps, sem_classes):
         super().__init__()
@@ -99,10 +106,10 @@ class Backbone(nn.Module):
             ME.MinkowskiConvolution(input_channel, m, kernel_size=3, dimension=3),
             UBlock([m * c for c in block_channels], ME.MinkowskiBatchNorm, block_reps, ResidualBlock),
             ME.MinkowskiBatchNorm(m), ME.MinkowskiReLU(inplace=True))
-        self.semantic_branch = nn.Sequential(nn.Linear(m, m), nn.BatchNorm1d(m), nn.ReLU(inplace=True),
-                                             nn.Linear(m, sem_classes))
-        self.offset_branch = nn.Sequential(nn.Linear(m, m), nn.BatchNorm1d(m), nn.ReLU(inplace=True),
-                                           nn.Linear(m, 3))
+        self.semantic_branch = nn.Sequential(PointLinear(m, m), nn.BatchNorm1d(m), nn.ReLU(inplace=True),
+                                             PointLinear(m, sem_classes))
+        self.offset_branch = nn.Sequential(PointLinear(m, m), nn.BatchNorm1d(m), nn.ReLU(inplace=True),
+                                           PointLinear(m, 3))
 
     def forward(self, voxel_features, voxel_coordinates, v2p_map, level_sizes=None):
         # the loader's voxels are unique by construction (sparse_quantize) and it reports the level sizes: no host
@@ -352,7 +359,7 @@ class HAIS(GeneralModel):
         m = cfg.m
         self.tiny_unet = TinyUnet(m)
         self.score_branch = nn.Linear(m, 1)
-        self.mask_branch = nn.Sequential(nn.Linear(m, m), nn.ReLU(inplace=True), nn.Linear(m, 1))
+        self.mask_branch = nn.Sequential(PointLinear(m, m), nn.ReLU(inplace=True), PointLinear(m, 1))
 
     def forward(self, data, rand=None):
         cfg = self.cfg

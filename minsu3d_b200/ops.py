@@ -405,6 +405,59 @@ def wgrad_ws_bytes(K, c_a, c_g):
 
 
 # ------------------------------------------------------------------------------------------
+# Point-wise linear heads (backbone.py:21-35: nn.Linear over [n_points, m]).  Forward and data gradient stay
+# torch/cuBLAS (library GEMMs); the WEIGHT gradient dW = dy^T x contracts over 400k points into a 16 x 20 matrix --
+# cuBLAS picks a SIMT split-K kernel for that shape (0.36 ms for one head) -- and is the K = 1 identity-map case of
+# the T3 weight gradient, so it runs on b2s_conv_wgrad_ws (deterministic, any channel count).
+# ------------------------------------------------------------------------------------------
+_IDENT = {}
+
+
+def _ident_pairs(n, device):
+    key = (n, device.index)
+    v = _IDENT.get(key)
+    if v is None:
+        if len(_IDENT) > 64:
+            _IDENT.clear()
+        v = _IDENT[key] = (torch.arange(n, dtype=I32, device=device), torch.tensor([0, n], dtype=I32, device=device))
+    return v
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gy @ weight
+        if ctx.needs_input_grad[1]:
+            n = x.size(0)
+            ident, koff = _ident_pairs(n, x.device)
+            gw = conv_wgrad(gy, x.contiguous(), ident, ident, koff, 1, weight.size(0), weight.size(1), n)[0]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gw, gb
+
+
+LINEAR_MIN_ROWS = 16384
+
+
+def linear(x, weight, bias=None):
+    """F.linear with the weight gradient on libb2s for tall fp32 CUDA inputs; plain F.linear otherwise."""
+    if (x.is_cuda and x.dim() == 2 and x.dtype == torch.float32 and x.size(0) >= LINEAR_MIN_ROWS
+            and torch.is_grad_enabled() and weight.requires_grad):
+        return _LinearFn.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------
 # T5 batch norm
 # ------------------------------------------------------------------------------------------
 _BN_COUNTERS = {}

@@ -151,7 +151,7 @@ def test_conv3_forward_backward(cin, cout, algo_name):
 
 
 WGRAD_SHAPES = [(16, 16), (32, 16), (16, 32), (32, 32), (48, 32), (48, 48), (64, 64), (80, 80), (96, 112), (224, 112),
-                (128, 256)]
+                (128, 256), (3, 16), (6, 16), (16, 20), (16, 3), (20, 24), (40, 1)]
 
 
 @pytest.mark.parametrize("ca,cg", WGRAD_SHAPES)
@@ -208,6 +208,26 @@ def test_wgrad_deterministic_small_and_identity(n):
         _close(gw1[0], want1)
     else:
         assert float(gw1.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 20), (16, 3), (16, 1)])
+def test_point_linear_matches_torch(cin, cout):
+    """ops.linear (harness heads): forward = F.linear bit for bit, gradients vs torch autograd in float64."""
+    from minsu3d_b200 import ops
+    torch.manual_seed(cin * 100 + cout)
+    n = 50_000
+    x = torch.randn(n, cin, device="cuda", requires_grad=True)
+    w = (torch.randn(cout, cin, device="cuda") / cin ** 0.5).requires_grad_()
+    b = torch.randn(cout, device="cuda", requires_grad=True)
+    g = torch.randn(n, cout, device="cuda")
+    y = ops.linear(x, w, b)
+    assert torch.equal(y, torch.nn.functional.linear(x, w, b))
+    y.backward(g)
+    xd, wd, bd = (t.detach().double().requires_grad_() for t in (x, w, b))
+    torch.nn.functional.linear(xd, wd, bd).backward(g.double())
+    _close(x.grad, xd.grad.cpu().numpy())
+    _close(w.grad, wd.grad.cpu().numpy())
+    _close(b.grad, bd.grad.cpu().numpy())
 
 
 @pytest.mark.parametrize("n", [1, 100, 5000, 150_000])

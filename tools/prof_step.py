@@ -21,6 +21,11 @@ else:
             tr.step(data)
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+    rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0 and not e.key.startswith(("autograd", "aten::", "_", "cuda"))]
+    print("=== device activities per step (name, launches, us)")
+    for k, c, t in sorted(rows, key=lambda r: -r[1]):
+        print("%6.1f %9.1f  %s" % (c / 2, t / 2, k[:110]))
+    print("launches per step", sum(r[1] for r in rows) / 2)
     import time
     t = time.perf_counter(); 
     for _ in range(3): tr.step(data)
