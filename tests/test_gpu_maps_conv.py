@@ -150,6 +150,23 @@ def test_conv3_forward_backward(cin, cout, algo_name):
     _close(gw, want_gw)
 
 
+@pytest.mark.parametrize("n,c", [(1, 16), (300, 16), (70_000, 16), (325_422, 16), (90_000, 32), (5000, 64), (300, 224)])
+def test_bn_one_launch_equals_two_kernel_path(n, c):
+    """b2s_bn_forward (one cooperative launch: statistics -> device-wide barrier -> apply) gives the same bits as
+    b2s_bn_stats followed by b2s_bn_apply (two kernels), running statistics included."""
+    from minsu3d_b200 import ops
+    torch.manual_seed(n + c)
+    x = torch.randn(n, c, device="cuda") * 3 + 1
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+    rm1, rv1 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    rm2, rv2 = rm1.clone(), rv1.clone()
+    y, mean, rstd = ops.bn_forward(x, 1e-4, 0.1, rm1, rv1, gamma, beta, True)
+    mean2, rstd2 = ops.bn_stats(x, 1e-4, 0.1, rm2, rv2)
+    y2 = ops.bn_apply(x, mean2, rstd2, gamma, beta, True)
+    for a, b in ((y, y2), (mean, mean2), (rstd, rstd2), (rm1, rm2), (rv1, rv2)):
+        assert torch.equal(a, b)
+
+
 WGRAD_SHAPES = [(16, 16), (32, 16), (16, 32), (32, 32), (48, 32), (48, 48), (64, 64), (80, 80), (96, 112), (224, 112),
                 (128, 256), (3, 16), (6, 16), (16, 20), (16, 3), (20, 24), (40, 1)]
 
