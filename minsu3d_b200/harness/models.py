@@ -7,6 +7,7 @@ hais,softgroup}.py (state-dict keys match: `backbone.unet.0.kernel`, `...conv_br
 but every sparse op goes through minsu3d_b200 (ME shim + common_ops mirror) and the clustering
 stage stays on the device: no `.cpu()` round trips (pointgroup.py:41-63 has six).
 """
+import os
 from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import List
@@ -89,6 +90,9 @@ class UBlock(nn.Module):
             out = self._bn_relu_conv(self.deconv, self.u(self._bn_relu_conv(self.conv, out)))
             out = self.blocks_tail(ME.cat(skip, out))
         return out
+
+
+EARLY_LOSSES = os.environ.get("B2S_EARLY_LOSSES", "1") != "0"
 
 
 class PointLinear(nn.Linear):
@@ -259,6 +263,8 @@ class GeneralModel(nn.Module):
                              data.get("voxel_level_sizes") if ASYNC_SIZES else None)
 
     def base_loss(self, data, out):
+        if "_base_losses" in out:  # already enqueued while the host waited for the clustering counts (forward)
+            return dict(out["_base_losses"])
         if out["semantic_scores"].is_cuda:  # fused libb2s kernels (torch's nll_loss reduction is one CTA: 0.67 ms)
             losses = {"semantic_loss": ops.cross_entropy(out["semantic_scores"], data["sem_labels"], ignore_index=-1)}
         else:
@@ -317,10 +323,18 @@ class PointGroup(GeneralModel):
         # both ball queries, then both BFS clusterings, each pair with ONE host read of its data-dependent sizes
         # (the reference-shaped single calls -- common_ops.ballquery_batch_p / pointgroup_ops.pg_bfs_cluster -- read
         # one count each; results are identical, tests/test_gpu_models.py)
+        grad_on = torch.is_grad_enabled()
         with torch.no_grad():
             shifted = (coords_ + offsets.detach()[object_idxs]).contiguous()
+            # the semantic / offset losses do not depend on the proposals: they are enqueued between the launch of the
+            # ball-query count passes and the host read of their results, so their ~1 ms of host work (60 small
+            # kernels) hides behind the GPU instead of delaying the backward
+            def early_losses():
+                if grad_on and self.training and EARLY_LOSSES:
+                    with torch.enable_grad():
+                        out["_base_losses"] = self.base_loss(data, out)
             queries = ops.ballquery_many([coords_.contiguous(), shifted], batch_idxs_.contiguous(), batch_offsets_,
-                                         cfg.cluster_radius)
+                                         cfg.cluster_radius, between=early_losses)
             sets = []
             for p_idx, p_off in ops.pg_cluster_many(sem_, queries, cfg.cluster_npoint_thre):
                 p_idx = p_idx.long()

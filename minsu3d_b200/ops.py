@@ -642,11 +642,12 @@ def ballquery(coords, batch_idxs, batch_offsets, radius):
     return idx, start_len
 
 
-def ballquery_many(coord_sets, batch_idxs, batch_offsets, radius):
+def ballquery_many(coord_sets, batch_idxs, batch_offsets, radius, between=None):
     """Several ball queries over the same points' batch layout (PointGroup: raw and shifted coordinates,
     pointgroup.py:43,58) with ONE host read for all pair counts instead of one per query: all count passes are
     enqueued first (each keeps its own cell grid), the counts are read together, then all fill passes run.
-    Returns [(idx, start_len), ...], identical to [ballquery(c, ...) for c in coord_sets]."""
+    Returns [(idx, start_len), ...], identical to [ballquery(c, ...) for c in coord_sets].
+    `between` (optional callable) runs after the count passes are enqueued and before their results are read."""
     require_cuda(batch_idxs, batch_offsets, *coord_sets)
     n = batch_idxs.numel()
     dev = batch_idxs.device
@@ -669,7 +670,10 @@ def ballquery_many(coord_sets, batch_idxs, batch_offsets, radius):
                   "ballquery_count")
         state.append((coords, start_len, d_count, ws))
     fork.join()
-    counts = torch.cat([st[2] for st in state]).tolist()
+    d_counts = torch.cat([st[2] for st in state])
+    if between is not None:
+        between()  # independent host work of the caller, enqueued while the count passes run
+    counts = d_counts.tolist()
     run_deferred_checks()
     out = []
     fork.begin()
