@@ -112,7 +112,9 @@ int b2s_pairs_from_nbr(const int32_t* nbr, int64_t n_out, int32_t K, int64_t pai
  *     transposed-conv forward and strided-conv data gradient.
  * b2s_conv_wgrad: gW[k] (+)= sum_p A[src[p], :]^T @ G[dst[p], :]   (gW zeroed by the callee)
  * algo: 0 = auto (tcgen05 3xTF32 when c_in, c_out are multiples of 16 and c_out <= 256, else fp32 FMA),
- *       1 = fp32 FMA (SIMT), 2 = tcgen05 3xTF32 (fp32-class accuracy), 3 = tcgen05 plain TF32.
+ *       1 = fp32 FMA (SIMT), 2 = tcgen05 3xTF32 (fp32-class accuracy), 3 = tcgen05 plain TF32,
+ *       4 = warp-stream mma.sync 3xTF32 kernel (csrc/conv_ws.cu; table mode, c_in, c_out in {16, 32}, K <= 32 only;
+ *           an explored alternative for the narrow layers, not chosen by auto).
  * ---------------------------------------------------------------------------------------------- */
 size_t b2s_conv_ws_bytes(int32_t K, int32_t c_in, int32_t c_out); /* scratch: packed weights + split partial sums */
 /* Packed weights.  The tcgen05 kernels read W as SWIZZLE_64B shared-memory images split into TF32 hi / lo parts.

@@ -14,7 +14,7 @@ PKG = os.path.dirname(HERE)
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libb2s.so")
 OBJ_DIR = os.path.join(PKG, "build")
-SOURCES = ["hash_map.cu", "tile_order.cu", "conv_simt.cu", "conv_tc.cu", "conv_tcp.cu", "wgrad_mma.cu", "wgrad_det.cu", "conv_api.cu", "fused.cu", "bn.cu", "ballquery.cu",
+SOURCES = ["hash_map.cu", "tile_order.cu", "conv_simt.cu", "conv_tc.cu", "conv_tcp.cu", "conv_ws.cu", "wgrad_mma.cu", "wgrad_det.cu", "conv_api.cu", "fused.cu", "bn.cu", "ballquery.cu",
            "cluster.cu", "segops.cu", "postproc.cu", "augment.cu", "loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "177"]

@@ -31,6 +31,11 @@ int conv_tcp(const float* A, const float* Bp, const int32_t* idx, const uint32_t
              const float* add_src, float* out, int64_t n_out, int K, int c_in, int c_out, int krev, int nsplit,
              void* split_ws, cudaStream_t stream);
 
+// narrow layers (c_in, c_out in {16, 32}): warp-stream mma.sync kernel (conv_ws.cu), 3xTF32
+bool conv_ws_supported(int K, int c_in, int c_out);
+int conv_ws(const float* A, const float* W, const int32_t* nbr, const int32_t* out_rows, const float* add_src, float* out,
+            int64_t n_out, int K, int c_in, int c_out, int wT, int krev, cudaStream_t stream);
+
 __global__ void __launch_bounds__(256)
     add_rows_kernel(float4* __restrict__ y, const float4* __restrict__ s, int64_t total4) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,6 +74,15 @@ int conv_table_tc(const float* A, const float* W, const float* Wp, const int32_t
     return B2S_E_WORKSPACE;
   }
   if (n_out == 0) return B2S_OK;
+  // warp-stream kernel for the narrow layers: explicit (algo 4) or, for 3xTF32 calls, switched on with B2S_CONV_WS=1
+  // (measured: faster than the tcgen05 kernel only for 32 -> 16 products, profiles/r02_conv_ws.txt; default off)
+  static const int ws_env = [] {
+    const char* e = getenv("B2S_CONV_WS");
+    return (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }();
+  if ((nsplit == 4 || (nsplit == 3 && ws_env)) && nbr != nullptr && W != nullptr && conv_ws_supported(K, c_in, c_out))
+    return conv_ws(A, W, nbr, out_rows, add_src, out, n_out, K, c_in, c_out, wT, krev, stream);
+  if (nsplit == 4) nsplit = 3;
   if (!tc_persistent()) {
     int rc = conv_tc(A, W, Wp, nbr, nullptr, nullptr, tile_mask, out_rows, out, n_out, 0, K, c_in, c_out, wT, krev, nsplit,
                      false, ws, ws_bytes, stream);
@@ -87,13 +101,14 @@ using namespace b2s;
 static int pick(int algo, int K, int c_in, int c_out, const char* what, int* nsplit) {
   bool ok = conv_tc_supported(K, c_in, c_out);
   if (algo == 0) algo = ok ? 2 : 1;
-  if ((algo == 2 || algo == 3) && !ok) {
+  if (algo == 4 && !conv_ws_supported(K, c_in, c_out)) ok = false;
+  if ((algo == 2 || algo == 3 || algo == 4) && !ok) {
     char buf[160];
     snprintf(buf, sizeof(buf), "%s: shape (K=%d, c_in=%d, c_out=%d) not supported by the tcgen05 path", what, K, c_in, c_out);
     set_error(buf);
     return -1;
   }
-  *nsplit = algo == 2 ? 3 : 1;
+  *nsplit = algo == 2 ? 3 : (algo == 4 ? 4 : 1);
   return algo;
 }
 
@@ -158,7 +173,7 @@ int b2s_conv_table_rows(const float* A, const float* W, const float* Wp, const i
     set_error("conv_table_rows: only the tcgen05 path takes a row permutation (c_in, c_out multiples of 16)");
     return B2S_E_INVALID;
   }
-  const int nsplit = (algo == 3) ? 1 : 3;
+  const int nsplit = (algo == 3) ? 1 : (algo == 4 ? 4 : 3);
   return conv_table_tc(A, W, Wp, nbr_sorted, tile_mask, out_rows, add_src, out, n_out, K, c_in, c_out, w_transposed,
                        k_reversed, nsplit, ws, ws_bytes, stream);
 }
@@ -172,6 +187,7 @@ int b2s_conv_pairs(const float* A, const float* W, const float* Wp, const int32_
     return B2S_E_INVALID;
   }
   int nsplit = 0;
+  if (algo == 4) algo = 2;  // the warp-stream kernel is table-mode only
   algo = pick(algo, K, c_in, c_out, "conv_pairs", &nsplit);
   if (algo < 0) return B2S_E_INVALID;
   if (algo >= 2)

@@ -204,7 +204,7 @@ def pairs_from_nbr(nbr, exact=False):
 # ------------------------------------------------------------------------------------------
 # T3 / T4 convolution products
 # ------------------------------------------------------------------------------------------
-ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_TF32 = 0, 1, 2, 3
+ALGO_AUTO, ALGO_SIMT, ALGO_TC_3XTF32, ALGO_TC_TF32, ALGO_WARP_STREAM = 0, 1, 2, 3, 4
 _default_algo = ALGO_AUTO
 
 

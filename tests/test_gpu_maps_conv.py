@@ -167,6 +167,35 @@ def test_bn_one_launch_equals_two_kernel_path(n, c):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 16), (16, 32), (32, 32)])
+@pytest.mark.parametrize("n", [1, 17, 5000, 60_000])
+def test_conv3_warp_stream_kernel(cin, cout, n):
+    """algo 4 (csrc/conv_ws.cu, mma.sync 3xTF32 straight from the gathered rows): forward with the residual add and the
+    data gradient (transposed weights, reversed offsets) vs the oracle at 1e-4, row-order and mask-sorted tables."""
+    from minsu3d_b200 import ops
+    rng = np.random.default_rng(cin * 100 + cout + n)
+    c = surface_voxels(rng, n)
+    n = c.shape[0]
+    nbr = oracle.kernel_map(c, c, 3, 1)
+    x = rng.standard_normal((n, cin)).astype(np.float32)
+    w = (rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32)
+    g = rng.standard_normal((n, cout)).astype(np.float32)
+    sc = rng.standard_normal((n, cout)).astype(np.float32)
+    want = oracle.conv_fwd(x, w, nbr, n) + sc
+    want_gin, _ = oracle.conv_bwd(x, w, g, nbr)
+    d_nbr = _dev(nbr)
+    tables = [(d_nbr, {})]
+    if n >= 32768:
+        perm, nbs, tms = ops.tile_order(d_nbr)
+        tables.append((nbs, dict(out_rows=perm, tile_mask=tms)))
+    for tb, kw in tables:
+        got = ops.conv_table(_dev(x), _dev(w), tb, n, 27, cin, cout, algo=ops.ALGO_WARP_STREAM, add_src=_dev(sc), **kw)
+        _close(got, want)
+        gin = ops.conv_table(_dev(g), _dev(w), tb, n, 27, cout, cin, w_transposed=True, k_reversed=True,
+                             algo=ops.ALGO_WARP_STREAM, **kw)
+        _close(gin, want_gin)
+
+
 WGRAD_SHAPES = [(16, 16), (32, 16), (16, 32), (32, 32), (48, 32), (48, 48), (64, 64), (80, 80), (96, 112), (224, 112),
                 (128, 256), (3, 16), (6, 16), (16, 20), (16, 3), (20, 24), (40, 1)]
 
