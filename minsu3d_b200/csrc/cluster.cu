@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(CL_THREADS) bfs_order_kernel(OrderArgs a) {
         const int u = out[2 * f + 1];
         const int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
         int j = lvl_end + a.cnt[off + f];
+        if (a.cnt[off + f] == (f + 1 < lvl_end ? a.cnt[off + f + 1] : total)) continue;  // no children: skip the rescan
         for (int e0 = 0; e0 < l; e0 += 32) {
           const int e = e0 + lane;
           bool child = false;
@@ -453,6 +454,7 @@ __global__ void __launch_bounds__(CL_THREADS) bfs_order_grid_kernel(GridOrderArg
   // a.cid[v]: cluster id while v is unvisited, -1 outside the kept clusters, -2 - cluster id once visited: one
   // read per edge decides "same cluster and unvisited" (members of a cluster share the seed's label, so the
   // label needs no separate check).  a.parent[v]: queue position of the first frontier node that lists v.
+  int32_t* remaining = a.seedcid;        // [nC] nodes of the cluster not yet placed (reuses seedcid after the prologue)
   int32_t* fstart = a.fstart;            // [2][n + 2] per-cluster start of the frontier, double-buffered per level
   int32_t* filled = a.filled;            // [2][n + 2] nodes of the cluster already placed
   const int fstride = n + 2;
@@ -471,6 +473,7 @@ __global__ void __launch_bounds__(CL_THREADS) bfs_order_grid_kernel(GridOrderArg
     const int sd = a.seeds[c];
     const int off = a.cluster_offsets[c];
     a.F0[c] = sd;
+    remaining[c] = a.cluster_offsets[c + 1] - off - 1;  // seedcid is free from here on (its last read is above)
     a.cid[sd] = -2 - c;
     a.cluster_idxs[2 * off] = c;
     a.cluster_idxs[2 * off + 1] = sd;
@@ -495,6 +498,11 @@ __global__ void __launch_bounds__(CL_THREADS) bfs_order_grid_kernel(GridOrderArg
       const int cu = -2 - a.cid[u];
       const int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
       if (lane == 0) a.cnt[f] = 0;
+      // every node of this cluster has been placed already: nothing left to claim.  On the shifted coordinates (lists
+      // of ~400 neighbours, 2-3 BFS levels) the last frontier holds most of a cluster and all of its scans are skipped.
+      // (remaining[] is updated in phase C, one device-wide barrier before this read; the per-level bookkeeping in
+      // fstart / filled is not yet complete when phase A starts)
+      if (__ldcg(remaining + cu) == 0) continue;
       // four independent (neighbour -> state) load chains per lane: the loop is latency-bound otherwise
       for (int e0 = lane; e0 < l; e0 += 128) {
         int w[4], st[4];
@@ -566,8 +574,11 @@ __global__ void __launch_bounds__(CL_THREADS) bfs_order_grid_kernel(GridOrderArg
     if (blockIdx.x == 0 && tid == 0) a.base[fsize] = total;
     __syncthreads();  // base[fb, fe) written by this block is read below
     for (int f = fb + wib; f < fe; f += CL_THREADS / 32) {
+      const int nchild = __ldcg(a.cnt + f);
+      if (nchild == 0) continue;  // no child claimed through this node: its list need not be read again
       const int u = F[f];
       const int c = -2 - a.cid[u];
+      if (lane == 0) atomicSub(remaining + c, nchild);
       const int s = __ldg(a.start_len + 2 * u), l = __ldg(a.start_len + 2 * u + 1);
       const int fsc = fs_cur[c];
       const int cstart = (fsc >= fb) ? a.base[fsc] : c0_base;  // fsc < fb only for c == c0
