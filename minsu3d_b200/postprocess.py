@@ -102,7 +102,8 @@ def _instances(keys, ids, conf, xyz, sem_labels, num_ignored, num_proposals, lab
         out["bbox"] = torch.zeros((0, 6), dtype=torch.float32, device=dev)
         return out
     if label is not None:
-        out["label_id"] = torch.full((n,), int(label), dtype=torch.int64, device=dev)
+        out["label_id"] = (label.to(torch.int64) if torch.is_tensor(label)
+                           else torch.full((n,), int(label), dtype=torch.int64, device=dev))
     else:
         first = point[offsets[:-1].long()]  # lowest point index of each instance (semantic_pred_labels[mask][0])
         out["label_id"] = sem_labels[first].long() - num_ignored + 1
@@ -142,34 +143,32 @@ def hais_pred_instances(xyz, scores, proposals_idx, num_proposals, mask_scores, 
 
 def softgroup_pred_instances(xyz, proposals_idx, num_points, cls_scores, iou_scores, mask_scores, instance_classes,
                              mask_thr, cls_thr, min_npoint):
-    """softgroup.py:269-313: one filter pass per instance class that has any proposal above the class-score
-    threshold (one host read decides which); output ordered by class, then proposal; label_id = class + 1."""
+    """softgroup.py:269-313.  The reference filters once per instance class (a Python loop over 18 classes with dense
+    [nProposal, N] masks); here every (class, proposal) candidate is one VIRTUAL proposal vp = class * nProposal +
+    proposal, so one pair sort / distinct-point count / instance extraction serves all classes (three host reads per
+    scene instead of ~110).  Output ordered by class, then proposal (= ascending vp); label_id = class + 1."""
     num_instances = cls_scores.size(0)
-    cls = cls_scores.softmax(1)
-    above = cls[:, :instance_classes] > cls_thr
-    active = above.any(0).tolist()
-    parts = []
-    for i in range(instance_classes):
-        if not active[i]:
-            continue
-        keys = _sorted_keys(proposals_idx, valid=mask_scores[:, i] > mask_thr)
-        npoint = proposal_npoint(keys, num_instances)
-        ids = torch.nonzero(above[:, i] & (npoint >= min_npoint)).view(-1)
-        if ids.numel() == 0:
-            continue
-        score = cls[:, i] * iou_scores[:, i].clamp(0, 1)
-        parts.append(_instances(keys, ids, score[ids], xyz, None, 0, num_instances, label=i + 1))
     dev = cls_scores.device
-    if not parts:
+    cls = cls_scores.softmax(1)
+    above = cls[:, :instance_classes] > cls_thr                                  # [P, C] candidates
+    prop = proposals_idx[:, 0].long()
+    # pair r is a point of candidate (class i, proposal prop[r]) iff the class-i mask keeps it and the candidate exists
+    member = (mask_scores[:, :instance_classes] > mask_thr) & above[prop]        # [S, C]
+    rows, klass = torch.nonzero(member, as_tuple=True)                           # host read 1: number of virtual pairs
+    vpairs = torch.stack((klass * num_instances + prop[rows], proposals_idx[rows, 1].long()), dim=1)
+    n_virtual = instance_classes * num_instances
+    keys = _sorted_keys(vpairs) if vpairs.size(0) else torch.empty(0, dtype=torch.int64, device=dev)
+    npoint = proposal_npoint(keys, n_virtual) if vpairs.size(0) else torch.zeros(n_virtual, dtype=I32, device=dev)
+    ids = torch.nonzero(above.t().reshape(-1) & (npoint >= min_npoint)).view(-1)   # host read 2: instances (class-major)
+    if ids.numel() == 0:
         return {"proposal": torch.zeros(0, dtype=I32, device=dev), "label_id": torch.zeros(0, dtype=torch.int64, device=dev),
                 "conf": torch.zeros(0, dtype=torch.float32, device=dev),
                 "bbox": torch.zeros((0, 6), dtype=torch.float32, device=dev),
                 "mask_points": torch.zeros(0, dtype=I32, device=dev), "mask_offsets": torch.zeros(1, dtype=I32, device=dev)}
-    out = {k: torch.cat([p[k] for p in parts]) for k in ("proposal", "label_id", "conf", "bbox", "mask_points")}
-    counts = torch.cat([(p["mask_offsets"][1:] - p["mask_offsets"][:-1]) for p in parts])
-    offsets = torch.zeros(counts.numel() + 1, dtype=I32, device=dev)
-    offsets[1:] = torch.cumsum(counts, 0)
-    out["mask_offsets"] = offsets
+    klass_of, prop_of = ids // num_instances, ids % num_instances
+    score = cls[prop_of, klass_of] * iou_scores[prop_of, klass_of].clamp(0, 1)
+    out = _instances(keys, ids, score, xyz, None, 0, n_virtual, label=klass_of + 1)
+    out["proposal"] = prop_of.to(I32)
     return out
 
 
