@@ -33,25 +33,6 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
-def _host_group(group):
-    """A process group that can reduce small CPU tensors: the data group itself when it is gloo, else a gloo side
-    group over the same ranks (created once per process; every rank constructs its GradBucketer, so the collective
-    `new_group` call is matched)."""
-    if not dist.is_initialized():
-        return None
-    if dist.get_backend(group) == "gloo":
-        return group
-    key = id(group)
-    g = _HOST_GROUPS.get(key)
-    if g is None:
-        ranks = dist.get_process_group_ranks(group) if group is not None else None
-        g = _HOST_GROUPS[key] = dist.new_group(ranks=ranks, backend="gloo")
-    return g
-
-
-_HOST_GROUPS = {}
-
-
 class GradBucketer:
     """Flat fp32 gradient buckets in reverse registration order (~ the order backward produces gradients).
 
@@ -65,9 +46,10 @@ class GradBucketer:
 
     Parameters that received no gradient on ANY rank keep `p.grad = None` after `finish()` -- the optimizer then
     skips them exactly as it does at world size 1 and as the reference's DDP(find_unused_parameters=True) does
-    (config/model/base.yaml:12-20): e.g. the ScoreNet in a step where no rank found a proposal.  Which parameters
-    are used is host knowledge on every rank, so the global OR is one tiny bit-mask all-reduce on the gloo side
-    group: no device read, the host does not wait for the backward."""
+    (config/model/base.yaml:12-20): e.g. the ScoreNet in a step where no rank found a proposal.  The global OR of
+    the per-parameter flags rides on the data group as one more (844-byte) all-reduce behind the buckets; only a rank
+    that itself has an unused parameter reads it back -- the common step has no host-side collective and no device
+    read (round 2 used a gloo all-reduce per step here: a host-level rendezvous of all ranks in every step)."""
 
     def __init__(self, params, bucket_mb=8.0, group=None, overlap=True):
         self.group = group
@@ -107,7 +89,7 @@ class GradBucketer:
             self.views.append(views)
         self._ready = [0] * len(self.buckets)
         self._index = {p: i for i, p in enumerate(self.params)}
-        self.host_group = _host_group(group)
+        self.flags = torch.zeros(len(self.params), dtype=torch.float32, device=self.params[0].device)
         if overlap:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -140,16 +122,14 @@ class GradBucketer:
             self._next += 1
             self.launched_in_backward += 1
 
-    def _global_used(self, used_local):
-        """OR over ranks of the per-parameter 'received a gradient' flags (host-side, 63 flags per int64 word)."""
-        words = [0] * ((len(used_local) + 62) // 63)
-        for i, u in enumerate(used_local):
-            if u:
-                words[i // 63] |= 1 << (i % 63)
-        t = torch.tensor(words, dtype=torch.int64)
-        dist.all_reduce(t, op=dist.ReduceOp.BOR, group=self.host_group)
-        words = t.tolist()
-        return [bool((words[i // 63] >> (i % 63)) & 1) for i in range(len(used_local))]
+    def _launch_used_flags(self, used_local):
+        """Start the SUM all-reduce of the per-parameter 'received a gradient' flags on the data group (same stream
+        and ordering as the gradient buckets; 4 bytes per parameter).  The result is only READ by ranks that have a
+        locally unused parameter: a rank whose parameters all received gradients already knows the global OR."""
+        host = torch.tensor([1.0 if u else 0.0 for u in used_local], dtype=torch.float32,
+                            pin_memory=self.flags.is_cuda)
+        self.flags.copy_(host, non_blocking=True)
+        self._handles.append(dist.all_reduce(self.flags, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def finish(self):
         """Launch the remaining buckets in order, wait for all of them, average, expose the reduced gradients."""
@@ -159,11 +139,15 @@ class GradBucketer:
         while self._next < len(self.buckets):
             self._launch(self._next)
             self._next += 1
-        used = self._global_used(used_local)
-        self.last_unused = used.count(False)
+        self._launch_used_flags(used_local)
         for h in self._handles:
             h.wait()
         torch._foreach_mul_(self.flats, 1.0 / self.world)
+        if all(used_local):
+            used = used_local  # the global OR contains this rank's flags: no read, the host does not wait
+        else:
+            used = [f > 0.5 for f in self.flags.tolist()]  # rare (a rank without proposals): one small device read
+        self.last_unused = used.count(False)
         for plist, views in zip(self.buckets, self.views):
             for p, v in zip(plist, views):
                 p.grad = v if used[self._index[p]] else None
