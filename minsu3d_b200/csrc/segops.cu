@@ -71,7 +71,22 @@ __global__ void __launch_bounds__(SEG_THREADS)
       for (int ch = ch0; ch < c; ch += cw) {
         float best = init;
         int bi = -1;
-        for (int r = b + ph; r < e; r += phases) {
+        // eight independent loads in flight per thread (the compare chain alone exposes one L2 round trip per row)
+        int r = b + ph;
+        for (; r + 7 * phases < e; r += 8 * phases) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldg(inp + (int64_t)(r + u * phases) * c + ch);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const bool better = (op == 0) ? (v[u] > best) : (v[u] < best);
+            if (better) {
+              best = v[u];
+              bi = r + u * phases;
+            }
+          }
+        }
+        for (; r < e; r += phases) {
           float v = __ldg(inp + (int64_t)r * c + ch);
           bool better = (op == 0) ? (v > best) : (v < best);
           if (better) {
@@ -124,7 +139,19 @@ __global__ void __launch_bounds__(SEG_THREADS)
     for (int ch = ch0; ch < c; ch += cw) {
       float best = -INFINITY;
       int bi = -1;
-      for (int r = b + ph; r < e; r += phases) {
+      int r = b + ph;
+      for (; r + 7 * phases < e; r += 8 * phases) {  // eight loads in flight (see seg_minmax_kernel)
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(inp + (int64_t)(r + u * phases) * c + ch);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (v[u] > best) {
+            best = v[u];
+            bi = r + u * phases;
+          }
+      }
+      for (; r < e; r += phases) {
         const float v = __ldg(inp + (int64_t)r * c + ch);
         if (v > best) {
           best = v;
@@ -285,11 +312,23 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     gather_rows_kernel(const float* __restrict__ feat, const int64_t* __restrict__ idx, int64_t total,
                        int c4, float4* __restrict__ out) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  int64_t r = t / c4;
-  int q = (int)(t - r * c4);
-  out[t] = __ldg((const float4*)feat + idx[r] * c4 + q);
+  // four independent (index -> row piece) chains per thread: one chain per thread keeps 32 KB per SM in flight, which
+  // two dependent DRAM latencies turn into ~3 TB/s (profiles/r02 roofline table: 0.44 of HBM)
+  const int64_t t0 = (int64_t)blockIdx.x * (blockDim.x * 4) + threadIdx.x;
+  int64_t src[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t t = t0 + (int64_t)u * blockDim.x;
+    const int64_t r = t / c4;
+    src[u] = t < total ? __ldg(idx + r) * c4 + (t - r * c4) : -1;
+  }
+  float4 v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (src[u] >= 0) v[u] = __ldg((const float4*)feat + src[u]);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (src[u] >= 0) out[t0 + (int64_t)u * blockDim.x] = v[u];
 }
 __global__ void __launch_bounds__(256)
     gather_rows_scalar_kernel(const float* __restrict__ feat, const int64_t* __restrict__ idx,
@@ -303,15 +342,25 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     scatter_add_rows_kernel(const float* __restrict__ grad, const int64_t* __restrict__ idx,
                             int64_t total, int c4, float* __restrict__ gfeat) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  int64_t r = t / c4;
-  int q = (int)(t - r * c4);
-  float4 v = __ldg((const float4*)grad + t);
-  float* dst = gfeat + (idx[r] * c4 + q) * 4;
-  // 16-byte vector reduction (sm_90+): one L2 atomic per 4 channels
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
+  const int64_t t0 = (int64_t)blockIdx.x * (blockDim.x * 4) + threadIdx.x;
+  int64_t dsti[4];
+  float4 v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int64_t t = t0 + (int64_t)u * blockDim.x;
+    const int64_t r = t / c4;
+    dsti[u] = t < total ? __ldg(idx + r) * c4 + (t - r * c4) : -1;
+    if (t < total) v[u] = __ldg((const float4*)grad + t);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (dsti[u] < 0) continue;
+    float* dst = gfeat + dsti[u] * 4;
+    // 16-byte vector reduction (sm_90+): one L2 atomic per 4 channels
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z),
+                 "f"(v[u].w)
+                 : "memory");
+  }
 }
 __global__ void __launch_bounds__(256)
     scatter_add_rows_scalar_kernel(const float* __restrict__ grad, const int64_t* __restrict__ idx,
@@ -571,7 +620,7 @@ int b2s_gather_rows(const float* feat, const int64_t* idx, int64_t n, int32_t c,
   if (n <= 0) return B2S_OK;
   if ((c & 3) == 0) {
     int64_t total = n * (c / 4);
-    gather_rows_kernel<<<(unsigned)cdiv(total, 256), 256, 0, stream>>>(feat, idx, total, c / 4, (float4*)out);
+    gather_rows_kernel<<<(unsigned)cdiv(total, 1024), 256, 0, stream>>>(feat, idx, total, c / 4, (float4*)out);
   } else {
     int64_t total = n * c;
     gather_rows_scalar_kernel<<<(unsigned)cdiv(total, 256), 256, 0, stream>>>(feat, idx, total, c, out);
@@ -584,7 +633,7 @@ int b2s_scatter_add_rows(const float* grad, const int64_t* idx, int64_t n, int32
   if (n <= 0) return B2S_OK;
   if ((c & 3) == 0) {
     int64_t total = n * (c / 4);
-    scatter_add_rows_kernel<<<(unsigned)cdiv(total, 256), 256, 0, stream>>>(grad, idx, total, c / 4, gfeat);
+    scatter_add_rows_kernel<<<(unsigned)cdiv(total, 1024), 256, 0, stream>>>(grad, idx, total, c / 4, gfeat);
   } else {
     int64_t total = n * c;
     scatter_add_rows_scalar_kernel<<<(unsigned)cdiv(total, 256), 256, 0, stream>>>(grad, idx, total, c, gfeat);
