@@ -498,17 +498,23 @@ using namespace b2s;
 
 extern "C" {
 
-// launch geometry of bn_colsum_kernel: rows per CTA (a multiple of the rows one load batch covers) and the grid
-static void bn_grid(int64_t n, int c, int unroll, int* chunk, int* nblk) {
+// launch geometry shared by the column-sum kernel and the one-launch kernels: as many equal CTAs as the cap allows -- a
+// whole number per SM (rounding the chunk to whole load batches left 212 CTAs on 148 SMs for the level-0 tensor).  Both
+// paths use the same chunks, so their partial sums and therefore their results are bit-identical.
+static void bn_grid_fused(int64_t n, int c, int cap, int* chunk, int* nblk) {
   const int c4 = c / 4;
   const int rpp = BN_THREADS / c4 > 0 ? BN_THREADS / c4 : 1;
-  const int64_t batch_rows = (int64_t)rpp * unroll;
-  const int gmax = c <= 32 ? 296 : (c <= 64 ? 148 : 74);  // wide rows: fewer partials for the one-CTA second stage
-  int64_t want = cdiv(n > 0 ? n : 1, batch_rows);
-  int64_t g = want < gmax ? want : gmax;
-  int64_t ch = cdiv(cdiv(n > 0 ? n : 1, g), batch_rows) * batch_rows;
+  // (<= 296 CTAs: b2s_bn_ws_bytes sizes the partial sums for that many; wide rows: fewer partials to sum per CTA)
+  const int gmax = std::min(std::min(cap, 296), c <= 32 ? 2 * sm_count() : (c <= 64 ? sm_count() : sm_count() / 2));
+  if (n < 1) n = 1;
+  int64_t g = std::max<int64_t>(1, std::min<int64_t>(gmax, n / (2 * (int64_t)rpp)));
+  const int64_t ch = cdiv(n, g);
   *chunk = (int)ch;
-  *nblk = (int)cdiv(n > 0 ? n : 1, ch);
+  *nblk = (int)cdiv(n, ch);
+}
+static void bn_grid(int64_t n, int c, int unroll, int* chunk, int* nblk) {
+  (void)unroll;
+  bn_grid_fused(n, c, 296, chunk, nblk);
 }
 
 size_t b2s_bn_ws_bytes(int64_t n, int32_t c) {
@@ -562,6 +568,7 @@ static bool bn_fused_on() {
 
 static size_t bn_fused_smem(int c) { return bn_smem(c) + (size_t)2 * c * 4; }
 
+
 // CTAs of bn_fused_kernel<MODE> that are resident at once on the current device with this much shared memory
 template <int MODE>
 static int bn_fused_capacity(int c) {
@@ -599,7 +606,7 @@ int b2s_bn_forward(const float* x, int64_t n, int32_t c, float eps, float moment
                    float* rstd, int32_t* counter, void* ws, size_t ws_bytes, b2s_stream_t stream) {
   if (bn_fused_on() && n > 0 && bn_check(n, c) == B2S_OK) {
     int chunk, nblk;
-    bn_grid(n, c, 8, &chunk, &nblk);
+    bn_grid_fused(n, c, bn_fused_capacity<0>(c), &chunk, &nblk);
     if (nblk <= bn_fused_capacity<0>(c) && ws_bytes >= (size_t)nblk * 2 * c * 8) {
       BnFusedArgs a{x, nullptr, nullptr, nullptr, nullptr, gamma, beta, nullptr, y, mean, rstd, running_mean, running_var,
                     (double*)ws, counter, n, c, chunk, relu, 1, eps, momentum};
@@ -649,7 +656,13 @@ int b2s_bn_backward_add(const float* x, const float* y, const float* dy, const f
     return B2S_E_WORKSPACE;
   }
   double* partial = (double*)ws;
-  if (bn_fused_on() && nblk <= bn_fused_capacity<1>(c)) {
+  if (bn_fused_on()) {
+    int fchunk, fnblk;
+    bn_grid_fused(n, c, bn_fused_capacity<1>(c), &fchunk, &fnblk);
+    chunk = fchunk;
+    nblk = fnblk;
+  }
+  if (bn_fused_on() && nblk <= bn_fused_capacity<1>(c) && ws_bytes >= (size_t)nblk * 2 * c * 8) {
     BnFusedArgs a{x, y, dy, mean, rstd, gamma, nullptr, add_src, dx, dbeta, dgamma, nullptr, nullptr,
                   partial, counter, n, c, chunk, relu, training, 0.f, 0.f};
     return bn_fused_launch<1>(a, nblk, stream);
