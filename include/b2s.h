@@ -166,12 +166,16 @@ int b2s_conv_wgrad_ws(const float* A, const float* G, const int32_t* src, const 
 size_t b2s_bn_ws_bytes(int64_t n, int32_t c);
 /* batch statistics: mean, biased variance (optional), rstd = 1/sqrt(var+eps) (optional); when
  * running_mean/var are given they are updated in place with `momentum` and the unbiased variance. */
-/* counter: one int32 on the device that is ZERO between launches (the last block to finish runs the
- * second reduction stage and resets it); a dedicated buffer, not part of the shared workspace.          */
+/* counter: one int32 on the device that is ZERO between launches; a dedicated buffer per stream, not part of the
+ * shared workspace.  b2s_bn_stats: the last block to finish runs the second reduction stage and resets it.
+ * b2s_bn_forward / b2s_bn_backward[_add]: ONE cooperative launch each -- per-CTA column sums, a device-wide barrier on
+ * this word (arrivals in the low half, departures in the high half, the last CTA to leave resets it), then every CTA
+ * sums the partials in the same fixed order and normalises / differentiates the rows it has just read.  Results are
+ * bit-identical to b2s_bn_stats + b2s_bn_apply; B2S_BN_FUSED=0 selects the two-kernel path.                      */
 int b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum, float* running_mean,
                  float* running_var, float* mean, float* var_biased, float* rstd, int32_t* counter,
                  void* ws, size_t ws_bytes, b2s_stream_t stream);
-/* b2s_bn_stats followed by b2s_bn_apply in one call (training-mode forward of BatchNorm(+ReLU)). */
+/* b2s_bn_stats followed by b2s_bn_apply in one call and one launch (training-mode forward of BatchNorm(+ReLU)). */
 int b2s_bn_forward(const float* x, int64_t n, int32_t c, float eps, float momentum,
                    float* running_mean, float* running_var, const float* gamma, const float* beta,
                    int32_t relu, float* y, float* mean, float* rstd, int32_t* counter,
