@@ -99,6 +99,12 @@ __device__ __forceinline__ int hash_lookup(const uint64_t* __restrict__ keys,
   }
 }
 
+// Library-owned buffer of B2S_COUNTERS int32 per (device, stream), zero when handed out.  Kernels that use it as arrival
+// counters reset every word they touched before they finish ("self-cleaning"), so consecutive launches on the stream can
+// share it without a memset in between.  nullptr when the allocation fails.
+constexpr size_t B2S_COUNTERS = 16384;
+int* zeroed_counters(cudaStream_t stream);
+
 // device-wide exclusive scan of int32 (CUB underneath), temp storage from the workspace
 size_t scan_ws_bytes(int64_t n);
 int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, size_t ws_bytes,

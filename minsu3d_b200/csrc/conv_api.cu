@@ -1,10 +1,30 @@
 // C-ABI dispatch for the sparse convolution products (b2s.h: T3 / T4).
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
 namespace b2s {
+int* zeroed_counters(cudaStream_t stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, int*> bufs;
+  const std::pair<int, cudaStream_t> key(current_device(), stream);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = bufs.find(key);
+  if (it != bufs.end()) return it->second;
+  int* p = nullptr;
+  if (cudaMalloc(&p, B2S_COUNTERS * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  cudaMemsetAsync(p, 0, B2S_COUNTERS * sizeof(int), stream);
+  bufs[key] = p;
+  return p;
+}
+
 int conv_table_simt(const float*, const float*, const int32_t*, float*, int64_t, int, int, int, int, int, cudaStream_t);
 int conv_pairs_simt(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, float*, int, int, int, int, int64_t, cudaStream_t);
 int conv_wgrad_simt(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, float*, int, int, int, int64_t, cudaStream_t);

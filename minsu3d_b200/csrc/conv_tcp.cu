@@ -68,6 +68,11 @@ struct TcpArgs {
   int splits;
   int n_tiles, n_items;
   int idx_bulk;               // nbr base is 16-byte aligned: index tiles are moved with cp.async.bulk
+  // offset split with the reduction folded in: the warp that delivers the LAST part of its 32 rows of a tile (arrival
+  // counter per (tile, warp), self-cleaning) adds the parts in ascending order (+ residual) and stores the final rows
+  float* final_out;           // NULL: partial sums only, tcp_split_reduce_kernel finishes
+  const float* final_add;
+  int* split_done;
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -271,7 +276,7 @@ __device__ __forceinline__ void conv_tcp_body(const TcpArgs& a) {
     };
 
     // ---- epilogue: TMEM -> registers -> (+ residual) -> global ----------------------------------------------
-    auto epilogue = [&](int e_T, int e_part, int64_t e_orow, int e_ab, uint32_t e_ph) {
+    auto epilogue = [&](int e_T, int e_part, int64_t e_orow, int e_ab, uint32_t e_ph, int e_tile) {
       if (e_T > 0) {
         mbar_wait(tfull_bar(e_ab), e_ph);
         tc_fence_after();
@@ -308,6 +313,36 @@ __device__ __forceinline__ void conv_tcp_body(const TcpArgs& a) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(aempty_bar(e_ab));
+      }
+      if (a.splits > 1 && a.final_out != nullptr) {
+        // same summation order as tcp_split_reduce_kernel (part 0, 1, ..., then the residual): identical bits, whichever
+        // part arrives last
+        __threadfence();
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) old = atomicAdd(a.split_done + e_tile * 4 + warp, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == a.splits - 1) {
+          __threadfence();
+          if (e_orow >= 0) {
+            const int64_t part_stride = a.n_out * a.c_out;
+            const float* p0 = a.out + e_orow * a.c_out;
+            float4* o = (float4*)(a.final_out + e_orow * a.c_out);
+            for (int col = 0; col < a.c_out; col += 4) {
+              float4 acc = __ldcg((const float4*)(p0 + col));
+              for (int sp = 1; sp < a.splits; ++sp) {
+                const float4 v = __ldcg((const float4*)(p0 + (int64_t)sp * part_stride + col));
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+              }
+              if (a.final_add != nullptr) {
+                const float4 v = __ldg((const float4*)(a.final_add + e_orow * a.c_out + col));
+                acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+              }
+              o[col >> 2] = acc;
+            }
+          }
+          if (lane == 0) a.split_done[e_tile * 4 + warp] = 0;
+        }
       }
     };
 
@@ -361,7 +396,7 @@ __device__ __forceinline__ void conv_tcp_body(const TcpArgs& a) {
         const uint32_t e_ph = (uint32_t)(n_acc / a.acc_bufs) & 1u;
         if (T > 0) ++n_acc;
         const int64_t e_orow = (r < rows) ? (orow_perm >= 0 ? (int64_t)orow_perm : row0 + r) : -1;
-        epilogue(T, a.splits > 1 ? item - tile * a.splits : 0, e_orow, e_ab, e_ph);
+        epilogue(T, a.splits > 1 ? item - tile * a.splits : 0, e_orow, e_ab, e_ph, tile);
       }
       cp_async_wait<0>();
     } else {
@@ -408,6 +443,7 @@ __device__ __forceinline__ void conv_tcp_body(const TcpArgs& a) {
         if (e_T > 0) ++n_acc;
         const int64_t e_orow = (r < rows) ? (orow_perm >= 0 ? (int64_t)orow_perm : row0 + r) : -1;
         const int e_part = a.splits > 1 ? item - tile * a.splits : 0;
+        const int e_tile = tile;
         // every index of this item has been read: release its tile, then start the next item's gathers before
         // draining the accumulator
         release_idx(item, g_it - 1);
@@ -418,7 +454,7 @@ __device__ __forceinline__ void conv_tcp_body(const TcpArgs& a) {
           if (T > 0) load_next(ra);
           if (T > 1) load_next(rb);
         }
-        epilogue(e_T, e_part, e_orow, e_ab, e_ph);
+        epilogue(e_T, e_part, e_orow, e_ab, e_ph, e_tile);
       }
     }
     tc_fence_before();
@@ -666,9 +702,23 @@ static int launch_tcp(TcpArgs a, void* split_ws, float* final_out, const float* 
   a.splits = splits;
   a.n_items = a.n_tiles * splits;
   a.idx_bulk = (a.idx != nullptr && (((uintptr_t)a.idx) & 15) == 0) ? 1 : 0;
+  a.final_out = nullptr;
+  a.final_add = nullptr;
+  a.split_done = nullptr;
   if (splits > 1) {
     a.out = (float*)split_ws;
     a.add_src = nullptr;
+    // B2S_TC_SPLIT_FOLD=1 folds the reduction into the kernel (last-arriving warp sums the parts): 72 launches less per
+    // PointGroup step but MEASURED SLOWER -- step 23.4 vs 22.1 ms: one warp adding 32 rows x splits parts serially at the
+    // end of a latency-bound kernel costs more than the 3 us reduce kernel that spreads the same reads over the GPU.
+    // Default: separate tcp_split_reduce_kernel launch.
+    if (tcp_env("B2S_TC_SPLIT_FOLD", 0) != 0 && (size_t)a.n_tiles * 4 <= B2S_COUNTERS) {
+      a.split_done = zeroed_counters(stream);
+      if (a.split_done != nullptr) {
+        a.final_out = final_out;
+        a.final_add = add_src;
+      }
+    }
   } else {
     a.out = final_out;
     a.add_src = add_src;
@@ -689,7 +739,7 @@ static int launch_tcp(TcpArgs a, void* split_ws, float* final_out, const float* 
   const int grid = std::min(a.n_items, slots);
   kern<<<grid, TC_THREADS, smem, stream>>>(a);
   int rc = check_launch("conv_tcp");
-  if (rc || splits == 1) return rc;
+  if (rc || splits == 1 || a.final_out != nullptr) return rc;
   const int64_t total4 = a.n_out * (a.c_out / 4);
   tcp_split_reduce_kernel<<<(unsigned)cdiv(total4, 256), 256, 0, stream>>>((const float4*)split_ws, (const float4*)add_src,
                                                                            (float4*)final_out, total4, splits);

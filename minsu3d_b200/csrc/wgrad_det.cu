@@ -29,9 +29,6 @@
 // the few thousand pairs of a coarse U-Net level still spread over all warps of many CTAs.
 #include <algorithm>
 #include <cstdlib>
-#include <map>
-#include <mutex>
-#include <utility>
 
 #include "common.cuh"
 
@@ -380,25 +377,6 @@ size_t conv_wgrad_det_ws_bytes(int K, int c_a, int c_g) {
   return need + 256;
 }
 
-constexpr size_t WD_COUNTERS = 16384;  // ints per (device, stream)
-
-static int* wd_counters(cudaStream_t stream) {
-  static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, int*> bufs;
-  const std::pair<int, cudaStream_t> key(current_device(), stream);
-  std::lock_guard<std::mutex> lock(mu);
-  auto it = bufs.find(key);
-  if (it != bufs.end()) return it->second;
-  int* p = nullptr;
-  if (cudaMalloc(&p, WD_COUNTERS * sizeof(int)) != cudaSuccess) {
-    cudaGetLastError();
-    return nullptr;
-  }
-  cudaMemsetAsync(p, 0, WD_COUNTERS * sizeof(int), stream);
-  bufs[key] = p;
-  return p;
-}
-
 template <int MT, int NT, int KB, int U, bool RAG>
 static int wd_launch(const WdShape& s, const float* A, const float* G, const int32_t* src, const int32_t* dst,
                      const int32_t* k_offsets, float* gW, float* part, int* done, int K, int c_a, int c_g,
@@ -452,7 +430,7 @@ int conv_wgrad_det(const float* A, const float* G, const int32_t* src, const int
   // counter), so they live in a small library-owned buffer per (device, stream) that is cleared once when it is
   // created: no memset per call (86 per PointGroup step).  Shapes with more counters than the buffer holds use the
   // head of the caller's workspace, which other products share, and clear it here.
-  int* done = (size_t)s.ty * s.tz * K <= WD_COUNTERS ? wd_counters(stream) : nullptr;
+  int* done = (size_t)s.ty * s.tz * K <= B2S_COUNTERS ? zeroed_counters(stream) : nullptr;
   if (done == nullptr) {
     done = (int*)ws;
     cudaMemsetAsync(done, 0, cnt_bytes, stream);
