@@ -419,7 +419,7 @@ def run_train(args, model_name):
                              "row counts of the strided maps are read back from the device (as the reference does); "
                              "voxel uniqueness is guaranteed by sparse_quantize and validated on the device"),
                    "conv_algo": "tcgen05 3xTF32 implicit GEMM, persistent kernel (fp32-class accuracy); fp32 FMA for the "
-                                "6-channel input conv and the weight gradient"},
+                                "3/6-channel input conv; weight gradient: deterministic mma.sync 3xTF32 (wgrad_det.cu)"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,

@@ -94,6 +94,16 @@ class UBlock(nn.Module):
 
 EARLY_LOSSES = os.environ.get("B2S_EARLY_LOSSES", "1") != "0"
 
+# what the backbone reads; Trainer.step_from_host copies these first and the rest of the batch on a copy stream
+BACKBONE_INPUTS = ("voxel_features", "voxel_xyz", "voxel_point_map", "voxel_level_sizes")
+
+
+def wait_late_inputs(data):
+    """Make the compute stream wait for the part of the batch that Trainer.step_from_host copies on its copy stream."""
+    ev = data.get("_late_event")
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
+
 
 class PointLinear(nn.Linear):
     """nn.Linear (same parameters / state-dict names) whose weight gradient over many points runs on libb2s."""
@@ -311,6 +321,7 @@ class PointGroup(GeneralModel):
     def forward(self, data, rand=None):
         cfg = self.cfg
         out = self.backbone_forward(data)
+        wait_late_inputs(data)
         if not self.clustering:
             return out
         scores, offsets = self._cluster_inputs(data, out)
@@ -378,6 +389,7 @@ class HAIS(GeneralModel):
     def forward(self, data, rand=None):
         cfg = self.cfg
         out = self.backbone_forward(data)
+        wait_late_inputs(data)
         if not self.clustering:
             return out
         scores, offsets = self._cluster_inputs(data, out)
@@ -511,6 +523,7 @@ class SoftGroup(GeneralModel):
     def forward(self, data, rand=None):
         cfg = self.cfg
         out = self.backbone_forward(data)
+        wait_late_inputs(data)
         if not self.clustering:
             return out
         scores, offsets = self._cluster_inputs(data, out)

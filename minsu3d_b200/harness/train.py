@@ -51,6 +51,8 @@ class Trainer:
         # host cost of the ~200-parameter step at a few launches (the default foreach path costs ~5 ms of Python)
         self.optimizer = torch.optim.Adam(self.model.parameters(), lr=cfg.lr, fused=(self.device.type == "cuda"))
         self.last_losses = None
+        self._copy_stream = None
+        self._copy_event = None
         # tensor-core operand images of every convolution kernel: refreshed in one launch after each optimizer step
         # (the modules would otherwise re-pack lazily, one launch per layer per step)
         self.packed = None
@@ -78,7 +80,28 @@ class Trainer:
 
     def step_from_host(self, host_data):
         """The user-facing call: pinned host batch in, python float loss out (H2D + D2H inside)."""
-        data = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_data.items()}
+        # the backbone needs only the voxel tensors: they are copied first on the compute stream; everything else
+        # (per-point labels, instance targets, point coordinates: ~half of the bytes) follows on a copy stream while
+        # the backbone forward is being enqueued and run; the model waits for it before its first use
+        # (models.wait_late_inputs, right after the backbone)
+        if self.device.type == "cuda":
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+                self._copy_event = torch.cuda.Event()
+            early = {k: v.to(self.device, non_blocking=True) for k, v in host_data.items()
+                     if torch.is_tensor(v) and k in models.BACKBONE_INPUTS}
+            main = torch.cuda.current_stream(self.device)
+            self._copy_stream.wait_stream(main)  # (the previous step's readers of recycled buffers have been enqueued)
+            with torch.cuda.stream(self._copy_stream):
+                late = {k: v.to(self.device, non_blocking=True) for k, v in host_data.items()
+                        if torch.is_tensor(v) and k not in models.BACKBONE_INPUTS}
+                self._copy_event.record(self._copy_stream)
+            for t in late.values():
+                t.record_stream(main)
+            data = {k: (early.get(k, late.get(k)) if torch.is_tensor(v) else v) for k, v in host_data.items()}
+            data["_late_event"] = self._copy_event
+        else:
+            data = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_data.items()}
         loss = float(self.step(data).item())
         ops.run_deferred_checks()  # size claims of this step (loader-reported level sizes), stream already drained
         return loss
