@@ -248,13 +248,16 @@ def get_segmented_scores(scores, fg_thresh=1.0, bg_thresh=0.0):
 
 
 def pt_offset_loss(pred_offsets, gt_offsets, valid_mask):
-    """minsu3d/loss/pt_offset_loss.py:12-38."""
-    if valid_mask.count_nonzero() == 0:
-        return 0, 0
-    p, g = pred_offsets[valid_mask], gt_offsets[valid_mask]
-    norm_loss = torch.sum(torch.abs(p - g), dim=-1).mean()
-    eps = torch.finfo(g.dtype).eps
-    dir_loss = -(F.normalize(g, p=2, dim=1, eps=eps) * F.normalize(p, p=2, dim=1, eps=eps)).sum(-1).mean()
+    """minsu3d/loss/pt_offset_loss.py:12-38.  Same means over the valid points, written as masked sums: the reference's
+    `pred[valid_mask]` costs two host reads (count_nonzero, the boolean index) and a sort-based index_put in the backward
+    (~0.3 ms per step); the masked form has no data-dependent shape.  No valid point -> both losses are 0 like the
+    reference's early return."""
+    m = valid_mask.to(pred_offsets.dtype)
+    cnt = m.sum().clamp(min=1.0)
+    norm_loss = (torch.sum(torch.abs(pred_offsets - gt_offsets), dim=-1) * m).sum() / cnt
+    eps = torch.finfo(gt_offsets.dtype).eps
+    cos = (F.normalize(gt_offsets, p=2, dim=1, eps=eps) * F.normalize(pred_offsets, p=2, dim=1, eps=eps)).sum(-1)
+    dir_loss = -(cos * m).sum() / cnt
     return norm_loss, dir_loss
 
 
