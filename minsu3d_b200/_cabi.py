@@ -131,7 +131,7 @@ class _Namespace:
 KERNELS_PER_CALL = {
     "b2s_coord_unique": 6, "b2s_kernel_map": 1, "b2s_pairs_from_nbr": 4, "b2s_conv_pack": 1, "b2s_conv_pack_multi": 1, "b2s_conv_table": 1, "b2s_conv_table_rows": 1, "b2s_tile_order": 7, "b2s_conv_pairs": 1,
     "b2s_conv_wgrad": 1, "b2s_conv_wgrad_ws": 1, "b2s_resblock_forward": 4, "b2s_resblock_backward": 6, "b2s_bnconv_forward": 2, "b2s_bnconv_backward": 3, "b2s_bn_backward_add": 1, "b2s_bn_stats": 1, "b2s_bn_forward": 1, "b2s_bn_apply": 1, "b2s_bn_backward": 1, "b2s_gather_rows": 1,
-    "b2s_scatter_add_rows": 1, "b2s_ballquery_count": 16, "b2s_ballquery_fill": 2, "b2s_cluster_label": 5,
+    "b2s_scatter_add_rows": 1, "b2s_ballquery_count": 16, "b2s_ballquery_fill": 2, "b2s_cluster_label": 6,
     "b2s_cluster_select": 7, "b2s_cluster_order": 4, "b2s_cluster_centers": 1, "b2s_ha_assign": 1,
     "b2s_ha_concat": 4, "b2s_sec_mean": 1, "b2s_sec_min": 1, "b2s_sec_max": 1, "b2s_roipool_fp": 1, "b2s_roipool_fp_ws": 2,
     "b2s_roipool_bp": 1, "b2s_global_avg_pool_fp": 1, "b2s_global_avg_pool_bp": 1, "b2s_get_iou": 1, "b2s_clusters_voxelize": 2,

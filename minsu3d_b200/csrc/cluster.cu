@@ -69,13 +69,14 @@ __device__ __forceinline__ int uf_find(int32_t* parent, int v) {
 __global__ void __launch_bounds__(256)
     cc_init_kernel(const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ start_len, int n,
                    int32_t* __restrict__ root, int32_t* __restrict__ m, int32_t* __restrict__ lastv,
-                   uint8_t* __restrict__ asym) {
+                   uint8_t* __restrict__ asym, int* __restrict__ n_capped) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
   m[v] = v;
   asym[v] = 0;
   const int s = __ldg(start_len + 2 * v), l = __ldg(start_len + 2 * v + 1);
   lastv[v] = (l >= BQ_LIST_CAP) ? __ldg(nbr_idx + s + l - 1) : 0x7fffffff;
+  if (l >= BQ_LIST_CAP) atomicAdd(n_capped, 1);  // rare; 0 = every list is complete, every edge symmetric
   root[v] = v;
 }
 
@@ -105,10 +106,11 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     cc_hook_kernel(const int32_t* __restrict__ nbr_idx, const int32_t* __restrict__ start_len,
                    const int16_t* __restrict__ labels, const int32_t* __restrict__ lastv, int n, int32_t* root,
-                   uint8_t* __restrict__ asym, int* __restrict__ n_asym) {
+                   uint8_t* __restrict__ asym, int* __restrict__ n_asym, const int* __restrict__ n_capped) {
   const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (u >= n) return;
+  const bool any_capped = *n_capped > 0;  // written by cc_init_kernel; uniform
   const int s = __ldg(start_len + 2 * u), l = __ldg(start_len + 2 * u + 1);
   const int lab = labels ? labels[u] : 0;
   bool directed = false;
@@ -117,8 +119,11 @@ __global__ void __launch_bounds__(256)
     // (unrolling this loop for memory-level parallelism was measured slower: prefetched roots go stale and the
     // shortcut below misses more often)
     const int w = __ldg(nbr_idx + s + e);
+    // without capped lists every edge is symmetric and the lower endpoint handles it: the edges towards lower indices
+    // (half of them) need no further read
+    if (!any_capped && w <= u) continue;
     if (labels && labels[w] != lab) continue;
-    if (u > __ldg(lastv + w)) {  // list(w) is capped and does not reach up to u
+    if (any_capped && u > __ldg(lastv + w)) {  // list(w) is capped and does not reach up to u
       directed = true;
       continue;
     }
@@ -815,10 +820,16 @@ int b2s_cluster_label(const int32_t* nbr_idx, const int32_t* start_len, const in
   int* flags = (int*)(bar + 2);
   int* n_asym = (int*)(bar + 8);
   cudaMemsetAsync(bar, 0, 64 * 4, stream);
-  cc_init_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(nbr_idx, start_len, (int)n, root, m, lastv, asym);
+  int* n_capped = (int*)(bar + 9);
+  cc_init_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(nbr_idx, start_len, (int)n, root, m, lastv, asym, n_capped);
   cc_prehook_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(nbr_idx, start_len, labels, lastv, (int)n, root);
+  // The pre-hook leaves chains (node -> lowest neighbour -> its lowest neighbour ...) as long as a cluster is wide in
+  // hops (~100 on raw coordinates); flattened here, every find of the hooking pass is one or two reads.  ncu of the
+  // raw-coordinate hook before this: 520 us for 1.17 M edges, 300 warps stalled on the scoreboard per issue
+  // (profiles/r02_cluster_kernels_ncu.txt).
+  cc_compress_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>((int)n, root);
   cc_hook_kernel<<<(unsigned)cdiv(n * 32, 256), 256, 0, stream>>>(nbr_idx, start_len, labels, lastv, (int)n, root, asym,
-                                                                  n_asym);
+                                                                  n_asym, n_capped);
   cc_compress_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>((int)n, root);
   int grid = coop_grid((const void*)cc_label_kernel, CL_THREADS, n * 32);
   int ni = (int)n;
