@@ -255,7 +255,8 @@ def test_cabi_size_queries_and_sass_is_blackwell_native():
     res = subprocess.run(["cuobjdump", "-sass", _cabi.LIB_PATH], capture_output=True, text=True)
     assert res.returncode == 0 and len(res.stdout) > 100_000, "cuobjdump produced no SASS: %s" % res.stderr[:200]
     # tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, cp.async.bulk -> UBLKCP, cp.async -> LDGSTS (B200_PROFILING.md)
-    counts = {m: res.stdout.count(m) for m in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "LDGSTS", "UTCBAR")}
+    # (+ HMMA: the mma.sync TF32 weight gradient / warp-stream convolution)
+    counts = {m: res.stdout.count(m) for m in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "LDGSTS", "UTCBAR", "HMMA")}
     for mnemonic, n in counts.items():
         assert n > 0, "%s missing from the SASS of libb2s.so (%s)" % (mnemonic, counts)
 
@@ -362,6 +363,28 @@ def test_segmented_scores_and_offset_loss_helpers():
     n, d = models.pt_offset_loss(torch.ones(4, 3), torch.ones(4, 3), torch.tensor([True, True, False, True]))
     assert float(n) == 0.0 and abs(float(d) + 1.0) < 1e-6
     assert models.pt_offset_loss(torch.ones(2, 3), torch.ones(2, 3), torch.tensor([False, False])) == (0, 0)
+
+
+def test_offset_loss_masked_form_equals_reference_indexing_form():
+    """harness.models.pt_offset_loss is written as masked means (no data-dependent shapes on the device); the
+    reference (minsu3d/loss/pt_offset_loss.py:12-38) indexes with the boolean mask.  Same values and gradients."""
+    import torch.nn.functional as F
+    from minsu3d_b200.harness import models
+    g = torch.Generator().manual_seed(0)
+    pred = torch.randn(5000, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    gt = torch.randn(5000, 3, generator=g, dtype=torch.float64)
+    mask = torch.rand(5000, generator=g) > 0.4
+    n_a, d_a = models.pt_offset_loss(pred, gt, mask)
+    (n_a + d_a).backward()
+    grad_a = pred.grad.clone()
+    pred.grad = None
+    p, q = pred[mask], gt[mask]
+    n_b = torch.sum(torch.abs(p - q), dim=-1).mean()
+    eps = torch.finfo(q.dtype).eps
+    d_b = -(F.normalize(q, p=2, dim=1, eps=eps) * F.normalize(p, p=2, dim=1, eps=eps)).sum(-1).mean()
+    (n_b + d_b).backward()
+    assert abs(float(n_a) - float(n_b)) < 1e-12 and abs(float(d_a) - float(d_b)) < 1e-12
+    assert torch.allclose(grad_a, pred.grad, rtol=0, atol=1e-14)
 
 
 # ------------------------------------------------------------------------------------------
